@@ -1,0 +1,46 @@
+// Instantiations of the fused cycle kernel, one translation unit per robot dof (OSC_INST_N)
+// so that nvcc compiles them in parallel.
+#include "osc_cycle.cuh"
+#include "osc_launch.h"
+
+#ifndef OSC_INST_N
+#error "compile with -DOSC_INST_N=<dof>"
+#endif
+
+namespace osc {
+
+template <int N, int R, bool JT>
+static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
+	const unsigned grid = (unsigned)((P.n_robots + kCycleBlock - 1) / kCycleBlock);
+	osc_cycle_kernel<N, R, JT><<<grid, kCycleBlock, 0, stream>>>(P);
+	return cudaGetLastError();
+}
+
+// motion-force task of rank R (1..min(6,N)), with or without a closing full joint task
+template <int N, int R>
+static cudaError_t launch_rank(bool has_jt, const OscProgram& P, cudaStream_t stream) {
+	if constexpr (R >= 1 && R <= N && R <= 6) {
+		return has_jt ? launch_one<N, R, true>(P, stream) : launch_one<N, R, false>(P, stream);
+	} else {
+		return cudaErrorNotSupported;
+	}
+}
+
+#define CONCAT_(a, b) a##b
+#define CONCAT(a, b) CONCAT_(a, b)
+
+cudaError_t CONCAT(launch_cycle_n, OSC_INST_N)(int R, bool has_jt, const OscProgram& P, cudaStream_t stream) {
+	constexpr int N = OSC_INST_N;
+	switch (R) {
+		case 0: return has_jt ? launch_one<N, 0, true>(P, stream) : cudaErrorNotSupported;
+		case 1: return launch_rank<N, 1>(has_jt, P, stream);
+		case 2: return launch_rank<N, 2>(has_jt, P, stream);
+		case 3: return launch_rank<N, 3>(has_jt, P, stream);
+		case 4: return launch_rank<N, 4>(has_jt, P, stream);
+		case 5: return launch_rank<N, 5>(has_jt, P, stream);
+		case 6: return launch_rank<N, 6>(has_jt, P, stream);
+	}
+	return cudaErrorNotSupported;
+}
+
+}  // namespace osc

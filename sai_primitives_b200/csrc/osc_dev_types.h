@@ -1,0 +1,119 @@
+// Device-side program description shared by the host layer (osc_capi.cu) and the kernels.
+// One OscProgram is passed to every kernel as a __grid_constant__ parameter, so its
+// members are served from the constant bank (warp-uniform broadcast reads).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/sai_b200_osc.h"
+
+// ---- SoA component layout of the per-robot MotionForceTask state block ----
+enum MftComp : int {
+	MC_GOAL_POS = 0,	  // 3
+	MC_GOAL_ORI = 3,	  // 9
+	MC_GOAL_LINVEL = 12,  // 3
+	MC_GOAL_ANGVEL = 15,  // 3
+	MC_GOAL_LINACC = 18,  // 3
+	MC_GOAL_ANGACC = 21,  // 3
+	MC_GOAL_FORCE = 24,	  // 3
+	MC_GOAL_MOMENT = 27,  // 3
+	MC_SENSED_F = 30,	  // 3  control point, world axes
+	MC_SENSED_M = 33,	  // 3
+	MC_SENSED_F_SENSOR = 36,
+	MC_SENSED_M_SENSOR = 39,
+	MC_INT_POS = 42,
+	MC_INT_ORI = 45,
+	MC_INT_FORCE = 48,
+	MC_INT_MOMENT = 51,
+	MC_CUR_POS = 54,	 // 3
+	MC_CUR_ORI = 57,	 // 9
+	MC_CUR_LINVEL = 66,	 // 3
+	MC_CUR_ANGVEL = 69,	 // 3
+	MC_UNIT_MASS_FORCE = 72, // 6
+	MC_ORI_ERROR = 78,	 // 3
+	MC_POPC = 81,		 // 4: PO, E_correction, Rc, sum vcl^2
+	MC_Q_PRIOR = 85,	 // OSC_MAX_DOF
+	MC_DQ_PRIOR = 93,	 // OSC_MAX_DOF
+	MC_TYPE2_DIR = 101,	 // OSC_MAX_DOF
+	MC_COUNT = 109
+};
+
+// int32 state components of a MotionForceTask
+enum MftIntComp : int {
+	MI_POPC_COUNTER = 0,
+	MI_RING_HEAD = 1,  // index of the oldest sample
+	MI_RING_SIZE = 2,
+	MI_T1_COUNTER = 3,
+	MI_T2_COUNTER = 4,
+	MI_HIST_HEAD = 5,
+	MI_HIST_SIZE = 6,
+	MI_N_TYPES = 7,	   // number of singular directions classified last update
+	MI_TYPES = 8,	   // 2 bits per direction
+	MI_HIST_BITS = 9,  // 8 words = 256 bits (bit = 1: type-1 entry)
+	MI_COUNT = 17
+};
+
+enum JtComp : int { JC_GOAL_POS = 0, JC_GOAL_VEL = 8, JC_GOAL_ACC = 16, JC_INT = 24, JC_COUNT = 32 };
+
+#define OSC_HIST_MAX 256
+
+struct DevModel {
+	int32_t n;
+	int32_t jtype[OSC_MAX_DOF];
+	double axis[OSC_MAX_DOF][3];
+	double R_fix[OSC_MAX_DOF][9];  // joint 0 has the world<-base transform folded in
+	double t_fix[OSC_MAX_DOF][3];
+	double mass[OSC_MAX_DOF];
+	double com[OSC_MAX_DOF][3];
+	double inertia[OSC_MAX_DOF][6];	 // xx xy xz yy yz zz
+	double q_lower[OSC_MAX_DOF], q_upper[OSC_MAX_DOF], effort[OSC_MAX_DOF];
+	double gravity[3];	// world frame
+};
+
+struct DevMft {
+	int32_t body;
+	int32_t rank, pos_range, ori_range;
+	int32_t full;		   // partial-task projection is the identity
+	int32_t in_compliant;  // force/motion spaces parametrised in the compliant frame
+	int32_t ring_capacity;
+	double ctrl_R[9], ctrl_t[3];  // compliant frame expressed in the body frame
+	double B[6][6];				  // orthonormal basis of the task range, 6 x rank (columns)
+	double Pt[9], Pr[9];		  // translation / rotation selection projectors
+	double cs_R[9], cs_t[3];	  // control frame -> sensor frame
+	double dt;
+	osc_mft_params p;
+	double* st;	   // MC_COUNT x N
+	int32_t* ist;  // MI_COUNT x N
+	double* ring;  // ring_capacity x N (or null)
+};
+
+struct DevJt {
+	int32_t k;
+	int32_t full;  // selection is the identity
+	double S[OSC_MAX_DOF][OSC_MAX_DOF];
+	double dt;
+	osc_joint_params p;
+	double* st;	 // JC_COUNT x N
+};
+
+struct DevTask {
+	int32_t type;  // osc_task_type
+	int32_t index; // index into mft[] / jt[]
+};
+
+struct OscProgram {
+	DevModel model;
+	int32_t n_tasks;
+	DevTask tasks[OSC_MAX_TASKS];
+	DevMft mft[2];
+	DevJt jt[2];
+	int32_t use_prev_torques;
+	int32_t gravity_comp;
+	int32_t torque_saturation;
+	int32_t update_models;	// this launch follows an updateControllerTaskModels()
+	int32_t write_observers;
+	int64_t n_robots;
+	const double* q;   // n x N
+	const double* dq;  // n x N
+	double* tau;	   // n x N
+	uint32_t* status;  // N
+};

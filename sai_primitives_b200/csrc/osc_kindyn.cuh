@@ -1,0 +1,221 @@
+// Per-robot kinematics / dynamics stage (north_star subsystem (a)): forward kinematics,
+// joint axes/origins for the 6 x n point Jacobian, composite-rigid-body mass matrix and
+// gravity vector of a serial chain, all in world coordinates.  Replaces what the reference
+// obtains from sai-model: updateModel / M / JWorldFrame / positionInWorld / rotationInWorld /
+// jointGravityVector (call sites: SURVEY.md section 8c).
+#pragma once
+#include "osc_dev_types.h"
+#include "osc_math.cuh"
+
+namespace osc {
+
+template <int N>
+struct KinDyn {
+	double a[N][3];	 // joint axis, world
+	double p[N][3];	 // joint origin (= body frame origin), world
+	double Rb[N][9]; // body orientation, world
+	double M[N][N];	 // joint-space mass matrix (full symmetric storage)
+	double g[N];	 // jointGravityVector
+};
+
+// Rotation about a unit axis (Rodrigues); exact pattern for coordinate axes.
+DEVI void axis_angle(const double ax[3], double s, double c, double R[9]) {
+	const double v = 1.0 - c;
+	const double x = ax[0], y = ax[1], z = ax[2];
+	R[0] = c + x * x * v;
+	R[1] = x * y * v - z * s;
+	R[2] = x * z * v + y * s;
+	R[3] = y * x * v + z * s;
+	R[4] = c + y * y * v;
+	R[5] = y * z * v - x * s;
+	R[6] = z * x * v - y * s;
+	R[7] = z * y * v + x * s;
+	R[8] = c + z * z * v;
+}
+
+template <int N>
+DEVI void forward_kinematics(const DevModel& m, const double (&q)[N], KinDyn<N>& kd) {
+	double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+	double p[3] = {0, 0, 0};
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		double t[3];
+		mat3_vec(R, m.t_fix[i], t);
+		p[0] += t[0];
+		p[1] += t[1];
+		p[2] += t[2];
+		double Rn[9];
+		mat3_mul(R, m.R_fix[i], Rn);
+		if (m.jtype[i] == 0) {
+			double s, c;
+			sincos(q[i], &s, &c);
+			double Rq[9];
+			axis_angle(m.axis[i], s, c, Rq);
+			mat3_mul(Rn, Rq, R);
+			mat3_vec(R, m.axis[i], kd.a[i]);
+		} else {
+#pragma unroll
+			for (int k = 0; k < 9; k++) R[k] = Rn[k];
+			mat3_vec(R, m.axis[i], kd.a[i]);
+			p[0] += kd.a[i][0] * q[i];
+			p[1] += kd.a[i][1] * q[i];
+			p[2] += kd.a[i][2] * q[i];
+		}
+#pragma unroll
+		for (int k = 0; k < 9; k++) kd.Rb[i][k] = R[k];
+		kd.p[i][0] = p[0];
+		kd.p[i][1] = p[1];
+		kd.p[i][2] = p[2];
+	}
+}
+
+// Composite rigid body algorithm with spatial inertias expressed about the world origin:
+// composite i = bodies i..N-1 as (mass, first moment h, second moment Ibar).
+template <int N, bool WITH_GRAVITY>
+DEVI void mass_matrix(const DevModel& m, KinDyn<N>& kd) {
+	double cm = 0.0, ch[3] = {0, 0, 0};
+	double cI[6] = {0, 0, 0, 0, 0, 0};	// xx xy xz yy yz zz
+#pragma unroll
+	for (int i = N - 1; i >= 0; i--) {
+		const double* R = kd.Rb[i];
+		// body inertia in world axes: R I R^T
+		const double* Ib = m.inertia[i];
+		double T[9];  // T = R * I
+#pragma unroll
+		for (int r = 0; r < 3; r++) {
+			T[3 * r + 0] = R[3 * r] * Ib[0] + R[3 * r + 1] * Ib[1] + R[3 * r + 2] * Ib[2];
+			T[3 * r + 1] = R[3 * r] * Ib[1] + R[3 * r + 1] * Ib[3] + R[3 * r + 2] * Ib[4];
+			T[3 * r + 2] = R[3 * r] * Ib[2] + R[3 * r + 1] * Ib[4] + R[3 * r + 2] * Ib[5];
+		}
+		double Iw[6];
+		Iw[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2];
+		Iw[1] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5];
+		Iw[2] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8];
+		Iw[3] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5];
+		Iw[4] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8];
+		Iw[5] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8];
+		double c[3];
+		mat3_vec(R, m.com[i], c);
+		c[0] += kd.p[i][0];
+		c[1] += kd.p[i][1];
+		c[2] += kd.p[i][2];
+		const double mi = m.mass[i];
+		const double cc = dot3(c, c);
+		cm += mi;
+		ch[0] += mi * c[0];
+		ch[1] += mi * c[1];
+		ch[2] += mi * c[2];
+		cI[0] += Iw[0] + mi * (cc - c[0] * c[0]);
+		cI[1] += Iw[1] - mi * c[0] * c[1];
+		cI[2] += Iw[2] - mi * c[0] * c[2];
+		cI[3] += Iw[3] + mi * (cc - c[1] * c[1]);
+		cI[4] += Iw[4] - mi * c[1] * c[2];
+		cI[5] += Iw[5] + mi * (cc - c[2] * c[2]);
+
+		// spatial motion of joint i about the world origin: (w, vo)
+		double w[3], vo[3];
+		if (m.jtype[i] == 0) {
+			w[0] = kd.a[i][0];
+			w[1] = kd.a[i][1];
+			w[2] = kd.a[i][2];
+			cross3(kd.p[i], kd.a[i], vo);
+		} else {
+			w[0] = w[1] = w[2] = 0.0;
+			vo[0] = kd.a[i][0];
+			vo[1] = kd.a[i][1];
+			vo[2] = kd.a[i][2];
+		}
+		// spatial momentum of the composite under that motion: linear f, angular no (about origin)
+		double f[3], no[3], t1[3];
+		cross3(w, ch, t1);
+		f[0] = cm * vo[0] + t1[0];
+		f[1] = cm * vo[1] + t1[1];
+		f[2] = cm * vo[2] + t1[2];
+		cross3(ch, vo, t1);
+		no[0] = cI[0] * w[0] + cI[1] * w[1] + cI[2] * w[2] + t1[0];
+		no[1] = cI[1] * w[0] + cI[3] * w[1] + cI[4] * w[2] + t1[1];
+		no[2] = cI[2] * w[0] + cI[4] * w[1] + cI[5] * w[2] + t1[2];
+#pragma unroll
+		for (int j = 0; j <= i; j++) {
+			double wj[3], voj[3];
+			if (m.jtype[j] == 0) {
+				wj[0] = kd.a[j][0];
+				wj[1] = kd.a[j][1];
+				wj[2] = kd.a[j][2];
+				cross3(kd.p[j], kd.a[j], voj);
+			} else {
+				wj[0] = wj[1] = wj[2] = 0.0;
+				voj[0] = kd.a[j][0];
+				voj[1] = kd.a[j][1];
+				voj[2] = kd.a[j][2];
+			}
+			const double v = dot3(wj, no) + dot3(voj, f);
+			kd.M[i][j] = v;
+			kd.M[j][i] = v;
+		}
+		if (WITH_GRAVITY) {
+			// -(s_i . gravity wrench of the composite about the origin)
+			double hg[3];
+			cross3(ch, m.gravity, hg);
+			kd.g[i] = -(dot3(w, hg) + cm * dot3(vo, m.gravity));
+		}
+	}
+}
+
+// 6 x n world-frame Jacobian (linear rows first) of point x fixed to body `body`,
+// stored transposed: JT[i][0..2] = linear column of joint i, JT[i][3..5] = angular.
+template <int N>
+DEVI void point_jacobian_t(const DevModel& m, const KinDyn<N>& kd, int body, const double x[3], double (&JT)[N][6]) {
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		if (i <= body) {
+			if (m.jtype[i] == 0) {
+				double d[3] = {x[0] - kd.p[i][0], x[1] - kd.p[i][1], x[2] - kd.p[i][2]};
+				double v[3];
+				cross3(kd.a[i], d, v);
+				JT[i][0] = v[0];
+				JT[i][1] = v[1];
+				JT[i][2] = v[2];
+				JT[i][3] = kd.a[i][0];
+				JT[i][4] = kd.a[i][1];
+				JT[i][5] = kd.a[i][2];
+			} else {
+				JT[i][0] = kd.a[i][0];
+				JT[i][1] = kd.a[i][1];
+				JT[i][2] = kd.a[i][2];
+				JT[i][3] = JT[i][4] = JT[i][5] = 0.0;
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < 6; k++) JT[i][k] = 0.0;
+		}
+	}
+}
+
+// pose of a frame (Rf, tf given in the body frame) in the world
+template <int N>
+DEVI void frame_pose(const KinDyn<N>& kd, int body, const double Rf[9], const double tf[3], double x[3], double R[9]) {
+	// body is warp-uniform but not a compile-time constant: select without dynamic indexing
+	double Rb[9], pb[3];
+#pragma unroll
+	for (int k = 0; k < 9; k++) Rb[k] = (k % 4 == 0) ? 1.0 : 0.0;	// body < 0: frame fixed to the world
+	pb[0] = pb[1] = pb[2] = 0.0;
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		if (i == body) {
+#pragma unroll
+			for (int k = 0; k < 9; k++) Rb[k] = kd.Rb[i][k];
+			pb[0] = kd.p[i][0];
+			pb[1] = kd.p[i][1];
+			pb[2] = kd.p[i][2];
+		}
+	}
+	double t[3];
+	mat3_vec(Rb, tf, t);
+	x[0] = pb[0] + t[0];
+	x[1] = pb[1] + t[1];
+	x[2] = pb[2] + t[2];
+	mat3_mul(Rb, Rf, R);
+}
+
+}  // namespace osc

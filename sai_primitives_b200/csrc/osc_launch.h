@@ -1,0 +1,28 @@
+// Host-callable launch wrappers around the templated kernels (implemented in the .cu files).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "osc_dev_types.h"
+
+namespace osc {
+
+constexpr int kCycleBlock = 128;
+
+// robot dofs the fused cycle kernel is instantiated for (one translation unit each, see Makefile)
+#define OSC_CYCLE_DOFS(X) X(4) X(6) X(7) X(8)
+
+// Fused control cycle for hierarchy signature (n, R, has_jt); cudaErrorNotSupported when the
+// signature is not compiled in (see osc_cycle_inst.inc).
+cudaError_t launch_cycle(int n, int R, bool has_jt, const OscProgram& P, cudaStream_t stream);
+bool cycle_signature_available(int n, int R, bool has_jt);
+
+cudaError_t launch_reinit_mft(const OscProgram& P, int mft_index, int full_init, cudaStream_t stream);
+cudaError_t launch_reinit_jt(const OscProgram& P, int jt_index, cudaStream_t stream);
+cudaError_t launch_sensed_wrench(const OscProgram& P, int mft_index, const double* f, const double* m, cudaStream_t stream);
+cudaError_t launch_eval_model(const OscProgram& P, const osc_link_frame& frame, double* M, double* J, double* x, double* R,
+							  double* g, cudaStream_t stream);
+cudaError_t launch_fill(double* st, int64_t NR, int comp, int ncomp, const double* vals, cudaStream_t stream);
+cudaError_t launch_copy(double* st, int64_t NR, int dst, int src, int ncomp, cudaStream_t stream);
+cudaError_t launch_fill_int(int32_t* ist, int64_t NR, int comp, int ncomp, int32_t value, cudaStream_t stream);
+
+}  // namespace osc

@@ -1,0 +1,250 @@
+// Small fixed-size FP64 linear algebra for one-robot-per-thread kernels.
+// Every loop bound is a template constant so that, after full unrolling, all array
+// indices are compile-time constants and the arrays live in registers (or spill to
+// thread-local memory under register pressure -- never dynamic indexing).
+#pragma once
+#include <cuda_runtime.h>
+
+#define DEVI __device__ __forceinline__
+
+namespace osc {
+
+DEVI void cross3(const double a[3], const double b[3], double o[3]) {
+	o[0] = a[1] * b[2] - a[2] * b[1];
+	o[1] = a[2] * b[0] - a[0] * b[2];
+	o[2] = a[0] * b[1] - a[1] * b[0];
+}
+DEVI double dot3(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// o = A(3x3 row-major) * v
+DEVI void mat3_vec(const double A[9], const double v[3], double o[3]) {
+	o[0] = A[0] * v[0] + A[1] * v[1] + A[2] * v[2];
+	o[1] = A[3] * v[0] + A[4] * v[1] + A[5] * v[2];
+	o[2] = A[6] * v[0] + A[7] * v[1] + A[8] * v[2];
+}
+// o = A^T * v
+DEVI void mat3t_vec(const double A[9], const double v[3], double o[3]) {
+	o[0] = A[0] * v[0] + A[3] * v[1] + A[6] * v[2];
+	o[1] = A[1] * v[0] + A[4] * v[1] + A[7] * v[2];
+	o[2] = A[2] * v[0] + A[5] * v[1] + A[8] * v[2];
+}
+// C = A * B (3x3 row-major)
+DEVI void mat3_mul(const double A[9], const double B[9], double C[9]) {
+#pragma unroll
+	for (int i = 0; i < 3; i++)
+#pragma unroll
+		for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+// C = A * B^T
+DEVI void mat3_mul_bt(const double A[9], const double B[9], double C[9]) {
+#pragma unroll
+	for (int i = 0; i < 3; i++)
+#pragma unroll
+		for (int j = 0; j < 3; j++)
+			C[3 * i + j] = A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1] + A[3 * i + 2] * B[3 * j + 2];
+}
+
+// In-place Cholesky of the lower triangle of a symmetric positive definite matrix: A = L L^T.
+// Returns false when a pivot is not positive (matrix not positive definite).
+template <int N>
+DEVI bool cholesky_lower(double (&A)[N][N]) {
+	bool ok = true;
+#pragma unroll
+	for (int j = 0; j < N; j++) {
+		double d = A[j][j];
+#pragma unroll
+		for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
+		ok = ok && (d > 0.0);
+		const double l = sqrt(d);
+		const double inv = 1.0 / l;
+		A[j][j] = l;
+#pragma unroll
+		for (int i = j + 1; i < N; i++) {
+			double s = A[i][j];
+#pragma unroll
+			for (int k = 0; k < j; k++) s -= A[i][k] * A[j][k];
+			A[i][j] = s * inv;
+		}
+	}
+	return ok;
+}
+
+// x <- L^-1 x   (L lower triangular, N x N)
+template <int N>
+DEVI void solve_lower(const double (&L)[N][N], double (&x)[N]) {
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		double s = x[i];
+#pragma unroll
+		for (int k = 0; k < i; k++) s -= L[i][k] * x[k];
+		x[i] = s / L[i][i];
+	}
+}
+// x <- L^-T x
+template <int N>
+DEVI void solve_lower_t(const double (&L)[N][N], double (&x)[N]) {
+#pragma unroll
+	for (int i = N - 1; i >= 0; i--) {
+		double s = x[i];
+#pragma unroll
+		for (int k = i + 1; k < N; k++) s -= L[k][i] * x[k];
+		x[i] = s / L[i][i];
+	}
+}
+// y = L x
+template <int N>
+DEVI void mul_lower(const double (&L)[N][N], const double (&x)[N], double (&y)[N]) {
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		double s = 0.0;
+#pragma unroll
+		for (int k = 0; k <= i; k++) s += L[i][k] * x[k];
+		y[i] = s;
+	}
+}
+// x <- (L L^T)^-1 x
+template <int N>
+DEVI void solve_spd(const double (&L)[N][N], double (&x)[N]) {
+	solve_lower<N>(L, x);
+	solve_lower_t<N>(L, x);
+}
+
+// x <- R^-T x  then  x <- R^-1 x  with R upper triangular R x R stored in X[C+i][j], i <= j
+// i.e. x <- (R^T R)^-1 x
+template <int N, int R, int C>
+DEVI void solve_rtr(const double (&X)[N][R], double (&x)[R]) {
+#pragma unroll
+	for (int i = 0; i < R; i++) {  // R^T z = x (forward)
+		double s = x[i];
+#pragma unroll
+		for (int k = 0; k < i; k++) s -= X[C + k][i] * x[k];
+		x[i] = s / X[C + i][i];
+	}
+#pragma unroll
+	for (int i = R - 1; i >= 0; i--) {	// R y = z (backward)
+		double s = x[i];
+#pragma unroll
+		for (int k = i + 1; k < R; k++) s -= X[C + i][k] * x[k];
+		x[i] = s / X[C + i][i];
+	}
+}
+
+// Householder QR of rows C..N-1 of X (N x R), in place:
+//   on exit X[C+i][j] (i <= j) holds R; reflector j is v_j with v_j[C+j] = vhead[j] and
+//   v_j[C+j+1..N-1] stored in X below the diagonal; H_j = I - beta[j] v_j v_j^T.
+template <int N, int R, int C>
+DEVI void householder_qr(double (&X)[N][R], double (&vhead)[R], double (&beta)[R]) {
+#pragma unroll
+	for (int j = 0; j < R; j++) {
+		constexpr int dummy = 0;
+		(void)dummy;
+		const int k = C + j;
+		double nrm2 = 0.0;
+#pragma unroll
+		for (int i = k; i < N; i++) nrm2 += X[i][j] * X[i][j];
+		const double nrm = sqrt(nrm2);
+		const double x0 = X[k][j];
+		const double alpha = (x0 >= 0.0) ? -nrm : nrm;
+		const double v0 = x0 - alpha;
+		// v^T v = nrm2 - 2 alpha x0 + alpha^2 = 2 (nrm2 - alpha x0)
+		const double vv = 2.0 * (nrm2 - alpha * x0);
+		const double b = (vv > 0.0) ? 2.0 / vv : 0.0;
+		vhead[j] = v0;
+		beta[j] = b;
+#pragma unroll
+		for (int jj = j + 1; jj < R; jj++) {
+			double s = v0 * X[k][jj];
+#pragma unroll
+			for (int i = k + 1; i < N; i++) s += X[i][j] * X[i][jj];
+			s *= b;
+			X[k][jj] -= s * v0;
+#pragma unroll
+			for (int i = k + 1; i < N; i++) X[i][jj] -= s * X[i][j];
+		}
+		X[k][j] = alpha;
+	}
+}
+
+// x <- H_1 ... H_R x   (reflectors from householder_qr, acting on rows C..N-1)
+template <int N, int R, int C>
+DEVI void apply_q(const double (&X)[N][R], const double (&vhead)[R], const double (&beta)[R], double (&x)[N]) {
+#pragma unroll
+	for (int j = R - 1; j >= 0; j--) {
+		const int k = C + j;
+		double s = vhead[j] * x[k];
+#pragma unroll
+		for (int i = k + 1; i < N; i++) s += X[i][j] * x[i];
+		s *= beta[j];
+		x[k] -= s * vhead[j];
+#pragma unroll
+		for (int i = k + 1; i < N; i++) x[i] -= s * X[i][j];
+	}
+}
+// x <- H_R ... H_1 x
+template <int N, int R, int C>
+DEVI void apply_qt(const double (&X)[N][R], const double (&vhead)[R], const double (&beta)[R], double (&x)[N]) {
+#pragma unroll
+	for (int j = 0; j < R; j++) {
+		const int k = C + j;
+		double s = vhead[j] * x[k];
+#pragma unroll
+		for (int i = k + 1; i < N; i++) s += X[i][j] * x[i];
+		s *= beta[j];
+		x[k] -= s * vhead[j];
+#pragma unroll
+		for (int i = k + 1; i < N; i++) x[i] -= s * X[i][j];
+	}
+}
+
+// Sufficient test for  s_min(J)/s_max(J) >= thr  on the R rows of J (stored as JT: N x R):
+// with G = J J^T,  lambda_max(G) <= (tr G^8)^(1/8) =: hi;  G - thr^2 hi I positive definite
+// implies lambda_min >= thr^2 hi >= thr^2 lambda_max.  Never accepts a singular robot;
+// rejects a thin band (< 1%) of non-singular ones, which then take the SVD path.
+template <int N, int R>
+DEVI bool sound_nonsingular(const double (&JT)[N][R], double thr, double abs_tol) {
+	double G[R][R];
+#pragma unroll
+	for (int a = 0; a < R; a++)
+#pragma unroll
+		for (int b = 0; b <= a; b++) {
+			double s = 0.0;
+#pragma unroll
+			for (int i = 0; i < N; i++) s += JT[i][a] * JT[i][b];
+			G[a][b] = s;
+			G[b][a] = s;
+		}
+	double tr = 0.0;
+#pragma unroll
+	for (int a = 0; a < R; a++) tr += G[a][a];
+	// sigma_0 >= sqrt(tr/R); require it comfortably above the absolute tolerance (SingularityHandler.cpp:83)
+	if (!(tr > (double)R * abs_tol * abs_tol)) return false;
+	if (R == 1) return true;
+	double G2[R][R];
+#pragma unroll
+	for (int a = 0; a < R; a++)
+#pragma unroll
+		for (int b = 0; b <= a; b++) {
+			double s = 0.0;
+#pragma unroll
+			for (int i = 0; i < R; i++) s += G[a][i] * G[i][b];
+			G2[a][b] = s;
+			G2[b][a] = s;
+		}
+	double t8 = 0.0;  // tr(G^8) = ||G^4||_F^2,  G^4 = G2*G2
+#pragma unroll
+	for (int a = 0; a < R; a++)
+#pragma unroll
+		for (int b = 0; b <= a; b++) {
+			double s = 0.0;
+#pragma unroll
+			for (int i = 0; i < R; i++) s += G2[a][i] * G2[i][b];
+			t8 += (a == b) ? s * s : 2.0 * s * s;
+		}
+	const double hi = sqrt(sqrt(sqrt(t8)));
+	const double shift = thr * thr * hi;
+#pragma unroll
+	for (int a = 0; a < R; a++) G[a][a] -= shift;
+	return cholesky_lower<R>(G);
+}
+
+}  // namespace osc

@@ -1,0 +1,172 @@
+"""Parity of the fused CUDA control cycle with the CPU restatement of the reference
+(oracle/primitives.py), through the C ABI.  Tolerance: 1e-9 relative per robot
+(BASELINE.json north_star), FP64."""
+import numpy as np
+import pytest
+
+from tests.osc_testlib import REL_TOL, TASK_POINTS, OracleBatch, rel_err, rng_for, rot_exp, sample_states
+
+pytestmark = pytest.mark.gpu
+
+DEC = [0, 1, 2]  # FULL_DYNAMIC_DECOUPLING, BOUNDED_INERTIA_ESTIMATES, IMPEDANCE
+
+
+def _set_joint_goals(jt_gpu, jt_or, q, n, with_vel=False):
+    N = q.shape[0]
+    gp = np.zeros((N, n)); gv = np.zeros((N, n)); ga = np.zeros((N, n))
+    for i in range(N):
+        g = rng_for(i, stream=1)
+        gp[i] = q[i] + g.uniform(-0.2, 0.2, n)
+        if with_vel:
+            gv[i] = g.uniform(-0.1, 0.1, n); ga[i] = g.uniform(-0.5, 0.5, n)
+        jt_or[i].setGoalPosition(gp[i]); jt_or[i].setGoalVelocity(gv[i]); jt_or[i].setGoalAcceleration(ga[i])
+    jt_gpu.setGoalPosition(gp); jt_gpu.setGoalVelocity(gv); jt_gpu.setGoalAcceleration(ga)
+
+
+def _set_mft_goals(mft_gpu, mft_or, N):
+    x0 = mft_gpu.getCurrentPosition(); R0 = mft_gpu.getCurrentOrientation()
+    xd = np.zeros((N, 3)); Rd = np.zeros((N, 3, 3)); vd = np.zeros((N, 3)); wd = np.zeros((N, 3)); ad = np.zeros((N, 3)); ald = np.zeros((N, 3))
+    for i in range(N):
+        g = rng_for(i, stream=2)
+        xd[i] = x0[i] + g.uniform(-0.05, 0.05, 3)
+        Rd[i] = R0[i] @ rot_exp(g.uniform(-0.2, 0.2, 3))
+        vd[i] = g.uniform(-0.1, 0.1, 3); wd[i] = g.uniform(-0.1, 0.1, 3)
+        ad[i] = g.uniform(-0.5, 0.5, 3); ald[i] = g.uniform(-0.5, 0.5, 3)
+        t = mft_or[i]
+        # goals are built from the GPU's own current pose: check the oracle agrees on it first
+        assert np.abs(t._current_position - x0[i]).max() < 1e-12
+        assert np.abs(t._current_orientation - R0[i]).max() < 1e-12
+        t.setGoalPosition(xd[i]); t.setGoalOrientation(Rd[i]); t.setGoalLinearVelocity(vd[i])
+        t.setGoalAngularVelocity(wd[i]); t.setGoalLinearAcceleration(ad[i]); t.setGoalAngularAcceleration(ald[i])
+    mft_gpu.setGoalPosition(xd); mft_gpu.setGoalOrientation(Rd); mft_gpu.setGoalLinearVelocity(vd)
+    mft_gpu.setGoalAngularVelocity(wd); mft_gpu.setGoalLinearAcceleration(ad); mft_gpu.setGoalAngularAcceleration(ald)
+
+
+@pytest.mark.parametrize("dec", DEC)
+@pytest.mark.parametrize("robot_name", ["panda", "rrrr"])
+def test_config1_joint_task_alone(robot_name, dec):
+    """BASELINE config 1: single full JointTask, kp 100 kv 20 (examples/01-joint_control/...cpp:133)."""
+    import sai_primitives_b200 as sp
+    N = 96
+    q, dq, _ = sample_states(robot_name, N)
+    n = q.shape[1]
+    robot = sp.BatchedRobot(robot_name, N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    jt = sp.JointTask(robot)
+    jt.setGains(100.0, 20.0, 3.0); jt.setDynamicDecouplingType(dec)
+    ctrl = sp.RobotController(robot, [jt])
+    ob = OracleBatch(robot_name, N); ob.set_state(q, dq)
+    ojt = ob.add_jt()
+    for t in ojt:
+        t.setGains(100.0, 20.0, 3.0); t.setDynamicDecouplingType(dec)
+    ob.finalize()
+    _set_joint_goals(jt, ojt, q, n, with_vel=True)
+    for cycle in range(3):   # the integrator state must evolve identically
+        ctrl.updateControllerTaskModels()
+        tau = ctrl.computeControlTorques()
+        ref = ob.cycle()
+        assert rel_err(tau, ref).max() < REL_TOL
+    assert (robot.status() == 0).all()
+
+
+@pytest.mark.parametrize("use_prev", [True, False])
+@pytest.mark.parametrize("dec", DEC)
+def test_config2_panda_osc_with_nullspace_joint_task(dec, use_prev):
+    """BASELINE config 2: MotionForceTask 6-DoF at end-effector (0,0,0.07) + JointTask in its null
+    space through RobotController (examples/05) and the manual sum of examples/04."""
+    import sai_primitives_b200 as sp
+    N = 128
+    q, dq, _ = sample_states("panda", N, min_sigma_ratio=0.075)
+    robot = sp.BatchedRobot("panda", N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    link, pt = TASK_POINTS["panda"]
+    mft = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt)))
+    jt = sp.JointTask(robot)
+    mft.setDynamicDecouplingType(dec); jt.setDynamicDecouplingType(dec)
+    ctrl = sp.RobotController(robot, [mft, jt], use_previous_torques=use_prev)
+    ob = OracleBatch("panda", N); ob.set_state(q, dq)
+    omft = ob.add_mft(link, (np.eye(3), np.array(pt))); ojt = ob.add_jt()
+    for a, b in zip(omft, ojt):
+        a.setDynamicDecouplingType(dec); b.setDynamicDecouplingType(dec)
+    ob.finalize()
+    _set_mft_goals(mft, omft, N); _set_joint_goals(jt, ojt, q, 7)
+    ctrl.updateControllerTaskModels()
+    tau = ctrl.computeControlTorques()
+    ref = ob.cycle(use_prev=use_prev)
+    st = robot.status()
+    handled = (st & sp.capi.STATUS_UNHANDLED) == 0
+    # the sound test may send a thin band of non-singular robots to the SVD path; nearly all stay
+    assert handled.mean() > 0.9
+    for i in np.nonzero(handled)[0]:
+        assert len(omft[i]._singularity_handler._singularity_types) == 0
+    assert rel_err(tau[handled], ref[handled]).max() < REL_TOL
+
+
+def test_config2_gravity_and_saturation():
+    import sai_primitives_b200 as sp
+    N = 64
+    q, dq, _ = sample_states("panda", N, min_sigma_ratio=0.075)
+    robot = sp.BatchedRobot("panda", N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    link, pt = TASK_POINTS["panda"]
+    mft = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt)))
+    jt = sp.JointTask(robot)
+    ctrl = sp.RobotController(robot, [mft, jt])
+    ctrl.enableGravityCompensation(True); ctrl.enableTorqueSaturation(True)
+    ob = OracleBatch("panda", N); ob.set_state(q, dq)
+    omft = ob.add_mft(link, (np.eye(3), np.array(pt))); ojt = ob.add_jt()
+    ob.finalize()
+    for c in ob.controllers:
+        c.enableGravityCompensation(True); c.enableTorqueSaturation(True)
+    _set_mft_goals(mft, omft, N); _set_joint_goals(jt, ojt, q, 7)
+    ctrl.updateControllerTaskModels()
+    tau = ctrl.computeControlTorques()
+    ref = ob.cycle()
+    handled = (robot.status() & sp.capi.STATUS_UNHANDLED) == 0
+    assert rel_err(tau[handled], ref[handled]).max() < REL_TOL
+    with pytest.raises(NotImplementedError):
+        ctrl.enableJointLimitAvoidance(True)
+
+
+@pytest.mark.parametrize("dec", DEC)
+@pytest.mark.parametrize("case", ["panda_xyz", "panda_yz_rotx", "rrrr_planar", "puma_full"])
+def test_partial_and_other_robots(case, dec):
+    """Partial MotionForceTasks (examples 08/09/11) and the other robots, JointTask in the null space."""
+    import sai_primitives_b200 as sp
+    cases = {
+        "panda_xyz": ("panda", [(1, 0, 0), (0, 1, 0), (0, 0, 1)], []),              # examples/09:114-121
+        "panda_yz_rotx": ("panda", [(0, 1, 0), (0, 0, 1)], [(1, 0, 0)]),             # examples/08:112-122
+        "rrrr_planar": ("rrrr", [(1, 0, 0), (0, 1, 0)], [(0, 0, 1)]),                # examples/11:105-115
+        "puma_full": ("puma_like", None, None),
+    }
+    robot_name, dt_, dr_ = cases[case]
+    N = 64
+    link, pt = TASK_POINTS[robot_name]
+    B = None
+    if dt_ is not None:
+        cols = [np.concatenate([np.array(v, float), np.zeros(3)]) for v in dt_] + \
+               [np.concatenate([np.zeros(3), np.array(v, float)]) for v in dr_]
+        B = np.array(cols).T
+    q, dq, _ = sample_states(robot_name, N, min_sigma_ratio=0.075, dirs=B)
+    n = q.shape[1]
+    robot = sp.BatchedRobot(robot_name, N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    mft = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt)), dt_, dr_)
+    jt = sp.JointTask(robot)
+    mft.setDynamicDecouplingType(dec); jt.setDynamicDecouplingType(dec)
+    ctrl = sp.RobotController(robot, [mft, jt])
+    ob = OracleBatch(robot_name, N); ob.set_state(q, dq)
+    omft = ob.add_mft(link, (np.eye(3), np.array(pt)), dt_, dr_); ojt = ob.add_jt()
+    for a, b in zip(omft, ojt):
+        a.setDynamicDecouplingType(dec); b.setDynamicDecouplingType(dec)
+    ob.finalize()
+    _set_mft_goals(mft, omft, N); _set_joint_goals(jt, ojt, q, n)
+    ctrl.updateControllerTaskModels()
+    tau = ctrl.computeControlTorques()
+    ref = ob.cycle()
+    st = robot.status()
+    handled = (st & sp.capi.STATUS_UNHANDLED) == 0
+    assert handled.mean() > 0.85
+    assert rel_err(tau[handled], ref[handled]).max() < REL_TOL
+    if robot_name == "puma_like":
+        assert ((st & sp.capi.STATUS_ZERO_RANGE) != 0).all()
