@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""Benchmark of the batched operational-space controller (BASELINE.json metric:
+robot control cycles/sec, batched OSC torques; p99 cycle latency).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--robots R] [--impl reference]
+
+A step = one control cycle (kinematics/dynamics -> task models -> torques) for one batch of
+R robots per GPU.  Workload (config.workload): BASELINE config 2 -- Panda, MotionForceTask 6-DoF at the
+end-effector + JointTask in its null space through RobotController, 65,536 robots per GPU (weak scaling:
+robots are sharded by batch index, one process per GPU, no collective on the control path).
+
+  value  whole-job cycles/s with q, dq, goals resident in HBM (device pointers through the C ABI);
+  e2e    the same metric through the C ABI with pinned HOST buffers: H2D of q, dq and D2H of tau inside
+         the timed region;
+  roofline  the fused kernel against the FP64 roofline (9.5 kFLOP per robot-cycle);
+  cpu_baseline  the C++ restatement of the reference path (oracle/cpp, kind "port": the reference itself
+         cannot be compiled here) looped over a bounded sample on the host cores.
+--impl reference runs only that CPU arm.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "robot_control_cycles_per_sec"
+UNIT = "cycles/s"
+FLOP_PER_CYCLE = 9.5e3
+FP64_PEAK_TFLOPS = 37.2       # 148 SM x 64 FMA/clk x 2 x 1.965 GHz (no FP64 entry in MEASURED_PEAKS.json)
+ROBOT = "panda"
+LINK, POINT = "end-effector", (0.0, 0.0, 0.07)
+SEED = 1234
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------ synthetic inputs
+def sample_batch(sp, n_robots, device, min_ratio=0.1):
+    """q ~ U(lo+0.1 range, hi-0.1 range), dq ~ U(-1,1); states whose task Jacobian has
+    s_min/s_max < min_ratio are rejected before timing so the timed path is the non-singular one.
+    The Jacobians of the candidates come from the library's own kinematics stage (input generation only)."""
+    desc = sp.capi.ModelDesc()
+    sp.capi.load_library().osc_builtin_model(ROBOT.encode(), C.byref(desc))
+    n = desc.n
+    lo = np.array(desc.q_lower[:n]); hi = np.array(desc.q_upper[:n])
+    rng = np.random.Generator(np.random.Philox(key=SEED))
+    q_ok = np.zeros((0, n)); dq_ok = np.zeros((0, n))
+    tried = 0
+    accepted = 0
+    chunk = 131072
+    probe = sp.BatchedRobot(ROBOT, chunk, device=device)
+    while q_ok.shape[0] < n_robots:
+        q = lo + (0.1 + 0.8 * rng.random((chunk, n))) * (hi - lo)
+        dq = rng.uniform(-1.0, 1.0, (chunk, n))
+        probe.setQ(q); probe.setDq(dq); probe.updateModel()
+        J = probe.evalModel(LINK, POINT)["J"]
+        w = np.linalg.eigvalsh(J @ J.transpose(0, 2, 1))
+        keep = np.sqrt(np.maximum(w[:, 0], 0) / w[:, -1]) >= min_ratio
+        q_ok = np.concatenate([q_ok, q[keep]]); dq_ok = np.concatenate([dq_ok, dq[keep]])
+        tried += chunk
+        accepted += int(keep.sum())
+    probe.close()
+    q_ok, dq_ok = q_ok[:n_robots], dq_ok[:n_robots]
+    return q_ok, dq_ok, 1.0 - accepted / max(tried, 1), rng
+
+
+def make_goals(rng, x, R, q):
+    N, n = q.shape
+    def expm(w):
+        th = np.linalg.norm(w, axis=1, keepdims=True)
+        k = w / np.maximum(th, 1e-12)
+        K = np.zeros((N, 3, 3))
+        K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
+        s, c = np.sin(th)[:, :, None], np.cos(th)[:, :, None]
+        return np.eye(3)[None] + s * K + (1 - c) * (K @ K)
+    return dict(
+        xd=x + rng.uniform(-0.05, 0.05, (N, 3)), Rd=R @ expm(rng.uniform(-0.2, 0.2, (N, 3))),
+        vd=rng.uniform(-0.1, 0.1, (N, 3)), wd=rng.uniform(-0.1, 0.1, (N, 3)),
+        ad=rng.uniform(-0.5, 0.5, (N, 3)), ald=rng.uniform(-0.5, 0.5, (N, 3)),
+        qd=q + rng.uniform(-0.2, 0.2, (N, n)))
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l for (t, l) in self.samples if t0 - 0.05 <= t <= t1 + 0.15] or [l for (_, l) in self.samples]
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arm
+def run_cpu_baseline(n_sample, target_seconds, q, dq, goals, threads=None):
+    """C++ restatement of the reference path (setQ/setDq/updateModel + updateControllerTaskModels +
+    computeControlTorques per robot) on the host cores; returns cycles/s and a description."""
+    from oracle.cpp_ref import CppOracleBatch
+    cb = CppOracleBatch(ROBOT, n_sample)
+    threads = threads or cb.hardware_threads()
+    cb.set_state(q[:n_sample], dq[:n_sample])
+    tm = cb.add_mft(LINK, (np.eye(3), np.array(POINT)))
+    tj = cb.add_jt()
+    g = goals
+    cb.mft_set_goals(tm, g["xd"][:n_sample], g["Rd"][:n_sample], g["vd"][:n_sample], g["wd"][:n_sample], g["ad"][:n_sample], g["ald"][:n_sample])
+    cb.jt_set_goals(tj, g["qd"][:n_sample])
+    cb.step(q[:n_sample], dq[:n_sample], n_threads=threads)   # warm-up
+    times = []
+    t_start = time.time()
+    while True:
+        t0 = time.perf_counter()
+        cb.step(q[:n_sample], dq[:n_sample], n_threads=threads)
+        times.append(time.perf_counter() - t0)
+        if time.time() - t_start > target_seconds and len(times) >= 3:
+            break
+    med = float(np.median(times))
+    cb.close()
+    return n_sample / med, med, len(times), threads
+
+
+def oracle_goals_numpy(q, dq, rng):
+    """goal generation for the CPU-only arm: poses from the numpy oracle's kinematics"""
+    from oracle.robots import make_chain
+    from oracle.sai_model import SaiModel
+    m = SaiModel(make_chain(ROBOT))
+    N = q.shape[0]
+    x = np.zeros((N, 3)); R = np.zeros((N, 3, 3))
+    for i in range(N):
+        m.setQ(q[i]); m.updateKinematics()
+        x[i] = m.positionInWorld(LINK, POINT); R[i] = m.rotationInWorld(LINK)
+    return make_goals(rng, x, R, q)
+
+
+def reference_arm(args):
+    """bench.py --impl reference: the reference's own CPU path (C++ port, all host threads) on a bounded
+    sample of the same workload.  No GPU, no product code."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.robots import make_chain
+    ch = make_chain(ROBOT)
+    n_sample = min(args.robots, 4096)
+    rng = np.random.Generator(np.random.Philox(key=SEED))
+    # same state distribution as the GPU arm: non-singular branch only (s_min/s_max >= 0.1), by rejection
+    from oracle.sai_model import SaiModel
+    probe = SaiModel(ch)
+    qs, dqs = [], []
+    while len(qs) < n_sample:
+        qc = ch.q_lower + (0.1 + 0.8 * rng.random(ch.n)) * (ch.q_upper - ch.q_lower)
+        dqc = rng.uniform(-1.0, 1.0, ch.n)
+        probe.setQ(qc); probe.updateKinematics()
+        sv = np.linalg.svd(probe.J(LINK, POINT), compute_uv=False)
+        if sv[-1] / sv[0] >= 0.1:
+            qs.append(qc); dqs.append(dqc)
+    q, dq = np.array(qs), np.array(dqs)
+    goals = oracle_goals_numpy(q, dq, rng)
+    from oracle.cpp_ref import CppOracleBatch
+    cb = CppOracleBatch(ROBOT, n_sample)
+    threads = cb.hardware_threads()
+    cb.set_state(q, dq)
+    tm = cb.add_mft(LINK, (np.eye(3), np.array(POINT))); tj = cb.add_jt()
+    cb.mft_set_goals(tm, goals["xd"], goals["Rd"], goals["vd"], goals["wd"], goals["ad"], goals["ald"]); cb.jt_set_goals(tj, goals["qd"])
+    for _ in range(max(args.warmup, 1)):
+        cb.step(q, dq, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cb.step(q, dq, n_threads=threads)
+    dt = time.perf_counter() - t0
+    value = n_sample * args.steps / dt
+    sample = "%d robots x %d cycles per run (same state filter as the GPU arm: s_min/s_max >= 0.1)" \
+             ", C++ port of the reference path, %d host threads" % (n_sample, args.steps, threads)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config2: Panda MotionForceTask 6-DoF + JointTask null space via RobotController, OTG off",
+                   "robots_per_step": n_sample, "note": "bounded sample of the GPU arm's workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import sai_primitives_b200 as sp
+    from sai_primitives_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = capi.load_library()
+    R = args.robots
+    n = 7
+    n_sets = args.sets
+
+    # ---- inputs: one accepted batch per rank (different Philox stream per rank), copied into n_sets controller
+    # instances so that consecutive steps touch different HBM (total working set > L2)
+    global SEED
+    SEED = 1234 + rank
+    t_gen = time.time()
+    q, dq, rejected, rng = sample_batch(sp, R, local_rank)
+    log("[rank %d] sampled %d non-singular states (rejected fraction %.3f) in %.1fs" % (rank, R, rejected, time.time() - t_gen))
+
+    # a dedicated (non-default) stream shared by torch and the library, so that torch.cuda.Event timing sees the kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sets = []
+    goals = None
+    for s in range(n_sets):
+        robot = sp.BatchedRobot(ROBOT, R, device=local_rank)
+        robot.setStream(stream.cuda_stream)
+        robot.setQ(q); robot.setDq(dq); robot.updateModel()
+        mft = sp.MotionForceTask(robot, LINK, (np.eye(3), np.array(POINT)))
+        jt = sp.JointTask(robot)
+        ctrl = sp.RobotController(robot, [mft, jt])
+        if goals is None:
+            goals = make_goals(rng, mft.getCurrentPosition(), mft.getCurrentOrientation(), q)
+        mft.setGoalPosition(goals["xd"]); mft.setGoalOrientation(goals["Rd"]); mft.setGoalLinearVelocity(goals["vd"])
+        mft.setGoalAngularVelocity(goals["wd"]); mft.setGoalLinearAcceleration(goals["ad"]); mft.setGoalAngularAcceleration(goals["ald"])
+        jt.setGoalPosition(goals["qd"])
+        d_q = torch.from_numpy(np.ascontiguousarray(q.T)).to(dev)      # SoA [n, R]
+        d_dq = torch.from_numpy(np.ascontiguousarray(dq.T)).to(dev)
+        d_tau = torch.zeros((n, R), dtype=torch.float64, device=dev)
+        sets.append(dict(robot=robot, ctrl=ctrl, q=d_q, dq=d_dq, tau=d_tau))
+    torch.cuda.synchronize()
+
+    def step_device(s):
+        rc = lib.osc_step(s["robot"].handle, C.c_void_p(s["q"].data_ptr()), C.c_void_p(s["dq"].data_ptr()),
+                          C.c_void_p(s["tau"].data_ptr()), capi.OSC_MEM_DEVICE)
+        if rc != 0:
+            raise RuntimeError(lib.osc_last_error(s["robot"].handle))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = sum(s["robot"].launchCount() for s in sets)
+    # ---- device-resident timing
+    for w in range(args.warmup):
+        step_device(sets[w % n_sets])
+    barrier()
+    launches0 = sum(s["robot"].launchCount() for s in sets)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.25)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        ev[k][0].record()
+        step_device(sets[k % n_sets])
+        ev[k][1].record()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    total_ms = e0.elapsed_time(e1)
+    launches = sum(s["robot"].launchCount() for s in sets) - launches0
+    per_step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # parity guard on the timed data: every robot stayed on the fast path and the torques are finite
+    st = sets[0]["robot"].status()
+    tau_host = sets[0]["tau"].cpu().numpy()
+    if (st & capi.STATUS_UNHANDLED).any() or not np.isfinite(tau_host).all():
+        raise SystemExit("bench: robots left the CUDA fast path (%d unhandled)" % int(((st & capi.STATUS_UNHANDLED) != 0).sum()))
+
+    # ---- end to end through the C ABI with pinned host buffers
+    hq = torch.from_numpy(np.ascontiguousarray(q.T)).pin_memory()
+    hdq = torch.from_numpy(np.ascontiguousarray(dq.T)).pin_memory()
+    htau = torch.zeros((n, R), dtype=torch.float64).pin_memory()
+
+    def step_host(s):
+        rc = lib.osc_step(s["robot"].handle, C.c_void_p(hq.data_ptr()), C.c_void_p(hdq.data_ptr()), C.c_void_p(htau.data_ptr()), capi.OSC_MEM_HOST)
+        if rc != 0:
+            raise RuntimeError(lib.osc_last_error(s["robot"].handle))
+
+    e2e_steps = max(3, min(args.steps, 50))
+    for w in range(3):
+        step_host(sets[w % n_sets])
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for k in range(e2e_steps):
+        step_host(sets[k % n_sets])
+    g1.record()
+    barrier()
+    e2e_ms = max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0))   # host-synchronous call: wall clock is the honest one
+    checksum = float(htau.sum())
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    value = world * R * args.steps / (total_ms * 1e-3)
+    e2e_value = world * R * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        kernel_ms = float(np.mean(per_step_ms))      # one launch per step: the CUDA-event bracket of a step is the kernel
+        achieved_tflops = FLOP_PER_CYCLE * R / (kernel_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        bytes_per_cycle = 8 * (14 + 24 + 21 + 2 * 13 + 7 + 12)   # q,dq + goals + integrators r/w + tau + pose observers
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config2: Panda MotionForceTask 6-DoF + JointTask null space via RobotController, OTG off, "
+                                   "BIE decoupling (reference defaults)",
+                       "robots_per_gpu": R, "robots_total": R * world,
+                       "l2": "inputs larger than L2: %d controller instances (%.0f MB of state) used round-robin" % (n_sets, n_sets * R * 8 * 250 / 1e6),
+                       "state_filter": "s_min/s_max >= 0.1 (non-singular branch), rejected fraction %.3f" % rejected,
+                       "parallelism": "robots sharded by batch index, %d process(es), no collective" % world},
+            "latency_ms": {"p50": float(np.percentile(per_step_ms, 50)), "p99": float(np.percentile(per_step_ms, 99)),
+                           "max": float(per_step_ms.max()), "samples": int(per_step_ms.size), "what": "CUDA events around one batched cycle, rank 0"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * n * R * 8), "d2h_bytes_per_step": int(n * R * 8),
+                    "steps": e2e_steps, "checksum": checksum},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / FP64_PEAK_TFLOPS, "traffic": None,
+                         "kernel": "osc_cycle_kernel<7,6,true>", "kernel_ms": kernel_ms,
+                         "flop_per_robot_cycle": FLOP_PER_CYCLE,
+                         "peak_source": "datasheet-derived FP64 FMA peak (148 SM x 64 FMA/clk x 2 x 1.965 GHz); MEASURED_PEAKS.json has no FP64 entry",
+                         "hbm": {"achieved_gbs": bytes_per_cycle * R / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                 "bytes_per_robot_cycle": bytes_per_cycle, "peak_source": "of measured" if peaks else "of fallback"}},
+        }
+        # CPU baseline on rank 0 at N=1 only
+        if world == 1 and not args.no_cpu:
+            n_sample = min(R, 4096)
+            v, med, reps, threads = run_cpu_baseline(n_sample, args.cpu_seconds, q, dq, goals)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": "%d robots of the same batch x 1 cycle, median of %d runs (%.3f s each), C++ restatement of "
+                                             "the reference path incl. model update, -O2, %d host threads" % (n_sample, reps, med, threads)}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--robots", type=int, default=65536, help="robots per GPU (BASELINE config 2: 65,536)")
+    ap.add_argument("--sets", type=int, default=8, help="controller instances used round-robin (working set > L2)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -193,7 +193,18 @@ class SingularityHandler:
         r = self._task_rank
         n = self._dof
         U, s, Vt = np.linalg.svd(projected_jacobian, full_matrices=False)
-        V = Vt.T
+        V = Vt.T.copy()
+        U = U.copy()
+        # SIGN CONVENTION (restatement decision): Eigen::JacobiSVD leaves the sign of each
+        # singular-vector pair unspecified, yet classifySingularity() below perturbs q by +5 rad along V_s[:, i]
+        # (:254), so the reference's type-1/type-2 decision depends on the sign its SVD happens to return.
+        # Every implementation in this repo orients each pair so that the largest-magnitude entry of V[:, i]
+        # is positive.
+        for k in range(V.shape[1]):
+            j = int(np.argmax(np.abs(V[:, k])))
+            if V[j, k] < 0:
+                V[:, k] = -V[:, k]
+                U[:, k] = -U[:, k]
         self._svd_U, self._svd_s, self._svd_V = U, s, V
         Minv = robot.MInv()
 
