@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsai_b200_osc.so")
+# SAI_B200_OSC_LIB selects another build of the SAME library (kernel tuning experiments); never a fallback
+LIB_PATH = os.environ.get("SAI_B200_OSC_LIB", os.path.join(_HERE, "libsai_b200_osc.so"))
 
 OSC_MAX_DOF = 8
 OSC_MAX_TASKS = 4

@@ -25,9 +25,23 @@
 // and handled by the SVD path.
 #pragma once
 #include "osc_kindyn.cuh"
+#include "osc_launch.h"
 #include "osc_tasks.cuh"
 
 namespace osc {
+
+// Optional re-convergence of the warps of a block at phase boundaries (so that they walk the large, fully
+// unrolled instruction stream together).  Measured on B200: no gain -- the instruction-fetch stalls of this
+// kernel are latency-, not bandwidth-bound (profiles/r01_v1_summary.md) -- so it is off; only legal when the
+// grid covers the batch exactly (the kernel returns early for out-of-range threads).
+#ifndef OSC_PHASE_SYNC
+#define OSC_PHASE_SYNC 0
+#endif
+#if OSC_PHASE_SYNC
+#define OSC_SYNC() __syncthreads()
+#else
+#define OSC_SYNC() ((void)0)
+#endif
 
 template <int N>
 DEVI void bie_cholesky(const double (&M)[N][N], double thr, double (&Lb)[N][N]) {
@@ -40,8 +54,11 @@ DEVI void bie_cholesky(const double (&M)[N][N], double thr, double (&Lb)[N][N]) 
 
 // Signature <N, R, HAS_JT>:  R = rank of a leading MotionForceTask (0: none),
 // HAS_JT = a full JointTask closes the hierarchy.
+#ifndef OSC_MIN_BLOCKS
+#define OSC_MIN_BLOCKS 1
+#endif
 template <int N, int R, bool HAS_JT>
-__global__ void __launch_bounds__(128) osc_cycle_kernel(const __grid_constant__ OscProgram P) {
+__global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(const __grid_constant__ OscProgram P) {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int64_t NR = P.n_robots;
 	if (i >= NR) return;
@@ -55,10 +72,12 @@ __global__ void __launch_bounds__(128) osc_cycle_kernel(const __grid_constant__ 
 	}
 	KinDyn<N> kd;
 	forward_kinematics<N>(mdl, q, kd);
+	OSC_SYNC();
 	if (P.gravity_comp)
 		mass_matrix<N, true>(mdl, kd);
 	else
 		mass_matrix<N, false>(mdl, kd);
+	OSC_SYNC();
 
 	double tau[N];
 #pragma unroll
@@ -74,6 +93,7 @@ __global__ void __launch_bounds__(128) osc_cycle_kernel(const __grid_constant__ 
 			for (int c = 0; c <= r; c++) L[r][c] = kd.M[r][c];
 		cholesky_lower<N>(L);
 	}
+	OSC_SYNC();
 
 	// Householder data of the motion-force task (kept for the joint task's null space)
 	double X[N][R > 0 ? R : 1];
@@ -102,9 +122,11 @@ __global__ void __launch_bounds__(128) osc_cycle_kernel(const __grid_constant__ 
 				}
 			}
 		if (!sound_nonsingular<N, R>(JtT, p.s_max, p.s_abs_tol)) status |= OSC_STATUS_SINGULAR_PATH | OSC_STATUS_UNHANDLED;
+	OSC_SYNC();
 
 		double fstar[6], F[6];
 		mft_control_law<N>(t, NR, i, x, Rc, JT0, dq, P.write_observers != 0, fstar, F, status);
+	OSC_SYNC();
 		double yf[R], yF[R];
 #pragma unroll
 		for (int a = 0; a < R; a++) {
@@ -135,12 +157,14 @@ __global__ void __launch_bounds__(128) osc_cycle_kernel(const __grid_constant__ 
 			}
 			householder_qr<N, R, 0>(X, vhead, beta);
 		}
+	OSC_SYNC();
 		if (p.dynamic_decoupling_type == OSC_FULL_DYNAMIC_DECOUPLING) {
 			solve_rtr<N, R, 0>(X, yf);
 		} else if (p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES) {
 			double Lb[N][N];
 			bie_cholesky<N>(kd.M, p.bie_threshold, Lb);
 			double Wb[N][R];
+	OSC_SYNC();
 #pragma unroll
 			for (int a = 0; a < R; a++) {
 				double col[N];
@@ -161,6 +185,7 @@ __global__ void __launch_bounds__(128) osc_cycle_kernel(const __grid_constant__ 
 					Ab[a][b] = s;
 				}
 			cholesky_lower<R>(Ab);
+	OSC_SYNC();
 			solve_spd<R>(Ab, yf);
 		}  // IMPEDANCE: Lambda_modified = I
 #pragma unroll
@@ -201,6 +226,7 @@ __global__ void __launch_bounds__(128) osc_cycle_kernel(const __grid_constant__ 
 		} else {
 			double pid[N], acc[N];
 			joint_control_law<N, N>(t, NR, i, q, dq, pid, acc);
+			OSC_SYNC();
 			// Q_perp = H_1..H_R [0; I],  W = L^-T Q_perp,  K = L Q_perp
 			double W[N][Mn], K[N][Mn];
 #pragma unroll
@@ -236,6 +262,7 @@ __global__ void __launch_bounds__(128) osc_cycle_kernel(const __grid_constant__ 
 			// ||N_prec||_F^2 = tr(G K^T K) must stay < 1e6 for the reference's 1e-3 range tolerance
 			if (!(nrm_chk < 1.0e6)) status |= OSC_STATUS_UNHANDLED;
 			cholesky_lower<Mn>(G);
+	OSC_SYNC();
 			// u = W^T (qdd_d - M^-1 tau_prec)
 			double rhs[N];
 #pragma unroll
@@ -268,6 +295,7 @@ __global__ void __launch_bounds__(128) osc_cycle_kernel(const __grid_constant__ 
 				double Lb[N][N];
 				bie_cholesky<N>(kd.M, p.bie_threshold, Lb);
 				double Z[N][Mn];
+	OSC_SYNC();
 #pragma unroll
 				for (int a = 0; a < Mn; a++) {
 					double col[N];

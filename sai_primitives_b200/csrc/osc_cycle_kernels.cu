@@ -7,6 +7,11 @@
 #error "compile with -DOSC_INST_N=<dof>"
 #endif
 
+// OSC_ONLY_R=<r> (tuning builds only): instantiate just the [MotionForceTask rank r, JointTask] kernel
+#ifndef OSC_ONLY_R
+#define OSC_ONLY_R 0
+#endif
+
 namespace osc {
 
 template <int N, int R, bool JT>
@@ -19,7 +24,10 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 // motion-force task of rank R (1..min(6,N)), with or without a closing full joint task
 template <int N, int R>
 static cudaError_t launch_rank(bool has_jt, const OscProgram& P, cudaStream_t stream) {
-	if constexpr (R >= 1 && R <= N && R <= 6) {
+	if constexpr (R >= 1 && R <= N && R <= 6 && OSC_ONLY_R != 0) {
+		if constexpr (R == OSC_ONLY_R) return has_jt ? launch_one<N, R, true>(P, stream) : cudaErrorNotSupported;
+		return cudaErrorNotSupported;
+	} else if constexpr (R >= 1 && R <= N && R <= 6) {
 		return has_jt ? launch_one<N, R, true>(P, stream) : launch_one<N, R, false>(P, stream);
 	} else {
 		return cudaErrorNotSupported;
@@ -32,7 +40,9 @@ static cudaError_t launch_rank(bool has_jt, const OscProgram& P, cudaStream_t st
 cudaError_t CONCAT(launch_cycle_n, OSC_INST_N)(int R, bool has_jt, const OscProgram& P, cudaStream_t stream) {
 	constexpr int N = OSC_INST_N;
 	switch (R) {
-		case 0: return has_jt ? launch_one<N, 0, true>(P, stream) : cudaErrorNotSupported;
+		case 0:
+			if constexpr (OSC_ONLY_R != 0) return cudaErrorNotSupported;
+			else return has_jt ? launch_one<N, 0, true>(P, stream) : cudaErrorNotSupported;
 		case 1: return launch_rank<N, 1>(has_jt, P, stream);
 		case 2: return launch_rank<N, 2>(has_jt, P, stream);
 		case 3: return launch_rank<N, 3>(has_jt, P, stream);

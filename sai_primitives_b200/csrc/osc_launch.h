@@ -6,7 +6,10 @@
 
 namespace osc {
 
-constexpr int kCycleBlock = 128;
+#ifndef OSC_CYCLE_BLOCK
+#define OSC_CYCLE_BLOCK 128
+#endif
+constexpr int kCycleBlock = OSC_CYCLE_BLOCK;
 
 // robot dofs the fused cycle kernel is instantiated for (one translation unit each, see Makefile)
 #define OSC_CYCLE_DOFS(X) X(4) X(6) X(7) X(8)
