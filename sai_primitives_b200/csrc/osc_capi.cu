@@ -43,6 +43,7 @@ struct osc_handle {
 	double *d_q = nullptr, *d_dq = nullptr, *d_tau = nullptr;
 	uint32_t* d_status = nullptr;
 	double *d_fs = nullptr, *d_ms = nullptr;  // staging for sensed wrench (3 x N each)
+	int32_t *d_sing_list = nullptr, *d_sing_count = nullptr;
 	std::vector<void*> allocations;
 	std::string err;
 	int64_t launches = 0;
@@ -354,6 +355,11 @@ int osc_create(const osc_model_desc* model, int64_t n_robots, int device, osc_ha
 	h->prog.dq = h->d_dq;
 	h->prog.tau = h->d_tau;
 	h->prog.status = h->d_status;
+	if ((rc = dev_alloc(h, &h->d_sing_list, (size_t)n_robots, true)) != OSC_OK) return cleanup(rc);
+	if ((rc = dev_alloc(h, &h->d_sing_count, (size_t)2, true)) != OSC_OK) return cleanup(rc);
+	h->prog.sing_list = h->d_sing_list;
+	h->prog.sing_count = h->d_sing_count;
+	h->prog.sing_parity = 0;
 	*out = h;
 	return OSC_OK;
 }
@@ -972,7 +978,8 @@ static int run_cycle(osc_handle* h, double* tau_out, int mem_kind) {
 	cudaError_t e = osc::launch_cycle(h->model.n, h->sig_R, h->sig_jt, h->prog, h->stream);
 	if (e == cudaErrorNotSupported) return fail(h, OSC_ERR_UNSUPPORTED, "no kernel compiled for this hierarchy signature");
 	CUDA_TRY(h, e);
-	h->launches++;
+	h->launches += (h->sig_R > 0) ? 2 : 1;  // fused cycle kernel (+ the SVD-path kernel when a motion-force task leads)
+	h->prog.sing_parity ^= 1;
 	if (mem_kind == OSC_MEM_HOST) {
 		CUDA_TRY(h, cudaMemcpyAsync(tau_out, h->d_tau, (size_t)h->model.n * h->NR * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
 		CUDA_TRY(h, cudaStreamSynchronize(h->stream));

@@ -61,6 +61,7 @@ template <int N, int R, bool HAS_JT>
 __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(const __grid_constant__ OscProgram P) {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int64_t NR = P.n_robots;
+	if (i == 0 && P.sing_count) P.sing_count[P.sing_parity ^ 1] = 0;
 	if (i >= NR) return;
 	const DevModel& mdl = P.model;
 
@@ -121,7 +122,32 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 					JtT[j][a] = s;
 				}
 			}
-		if (!sound_nonsingular<N, R>(JtT, p.s_max, p.s_abs_tol)) status |= OSC_STATUS_SINGULAR_PATH | OSC_STATUS_UNHANDLED;
+		// Branch decision of SingularityHandler::updateTaskModel (:83-105), taken before any task state is touched:
+		// robots that are not provably non-singular are appended (warp-aggregated) to the list of the SVD kernel
+		// and leave this kernel.
+		const bool flagged = !sound_nonsingular<N, R>(JtT, p.s_max, p.s_abs_tol);
+		{
+			const unsigned act = __activemask();
+			const unsigned m = __ballot_sync(act, flagged);
+			if (flagged) {
+				const int lane = threadIdx.x & 31;
+				const int leader = __ffs(m) - 1;
+				int base = 0;
+				if (lane == leader) base = atomicAdd(&P.sing_count[P.sing_parity], __popc(m));
+				base = __shfl_sync(m, base, leader);
+				P.sing_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+				return;
+			}
+		}
+		// classifySingularity with an empty singular range clears the handler memory (:239-245); only robots that
+		// were singular at the previous update have anything to clear
+		if (P.update_models && t.ist[(int64_t)MI_N_TYPES * NR + i] != 0) {
+			t.ist[(int64_t)MI_N_TYPES * NR + i] = 0;
+			t.ist[(int64_t)MI_T1_COUNTER * NR + i] = 0;
+			t.ist[(int64_t)MI_T2_COUNTER * NR + i] = 0;
+			t.ist[(int64_t)MI_HIST_HEAD * NR + i] = 0;
+			t.ist[(int64_t)MI_HIST_SIZE * NR + i] = 0;
+		}
 	OSC_SYNC();
 
 		double fstar[6], F[6];

@@ -1,6 +1,7 @@
 // Instantiations of the fused cycle kernel, one translation unit per robot dof (OSC_INST_N)
 // so that nvcc compiles them in parallel.
 #include "osc_cycle.cuh"
+#include "osc_singular.cuh"
 #include "osc_launch.h"
 
 #ifndef OSC_INST_N
@@ -18,6 +19,12 @@ template <int N, int R, bool JT>
 static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 	const unsigned grid = (unsigned)((P.n_robots + kCycleBlock - 1) / kCycleBlock);
 	osc_cycle_kernel<N, R, JT><<<grid, kCycleBlock, 0, stream>>>(P);
+	if constexpr (R > 0) {
+		// the SVD path for the robots the fast kernel handed over (usually none or few: exits immediately)
+		const long long want = (P.n_robots + 63) / 64;
+		const unsigned sgrid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+		osc_singular_kernel<N, R, JT><<<sgrid, 64, 0, stream>>>(P);
+	}
 	return cudaGetLastError();
 }
 

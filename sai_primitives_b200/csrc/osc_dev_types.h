@@ -116,4 +116,9 @@ struct OscProgram {
 	const double* dq;  // n x N
 	double* tau;	   // n x N
 	uint32_t* status;  // N
+	// robots that need the singular (SVD) path this cycle: compacted list + two counters used alternately
+	// (the fast kernel of cycle c fills count[c & 1] and clears count[(c + 1) & 1])
+	int32_t* sing_list;	  // N
+	int32_t* sing_count;  // 2
+	int32_t sing_parity;
 };

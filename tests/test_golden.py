@@ -103,10 +103,12 @@ def test_gpu_reproduces_config2_and_mixed_dof():
     for k in range(3):
         ctrl.updateControllerTaskModels()
         tau = ctrl.computeControlTorques()
-        handled = (robot.status() & sp.capi.STATUS_UNHANDLED) == 0
-        assert not (handled & d["singular"]).any()            # never treats a singular robot as non-singular
-        assert handled[~d["singular"]].mean() > 0.8
-        assert rel_err(tau[handled], d["tau"][k][handled]).max() < REL_TOL
+        st = robot.status()
+        assert (st & sp.capi.STATUS_UNHANDLED).sum() == 0
+        on_svd_path = (st & sp.capi.STATUS_SINGULAR_PATH) != 0
+        assert on_svd_path[d["singular"]].all()               # never treats a singular robot as non-singular
+        assert on_svd_path[~d["singular"]].mean() < 0.2       # the sound test rejects only a thin band
+        assert rel_err(tau, d["tau"][k]).max() < REL_TOL      # blending branch, type-1/type-2 strategies included
     m = load("config4_mixed_dof.npz")
     for name, dt_, dr_ in (("rrrr", [(1, 0, 0), (0, 1, 0)], [(0, 0, 1)]), ("puma_like", None, None)):
         goals = {k: m[name + "_" + k] for k in ("xd", "Rd", "vd", "wd", "ad", "ald", "qd")}
@@ -114,10 +116,10 @@ def test_gpu_reproduces_config2_and_mixed_dof():
         for k in range(3):
             ctrl.updateControllerTaskModels()
             tau = ctrl.computeControlTorques()
-            handled = (robot.status() & sp.capi.STATUS_UNHANDLED) == 0
-            assert not (handled & m[name + "_singular"]).any()
-            if handled.any():
-                assert rel_err(tau[handled], m[name + "_tau"][k][handled]).max() < REL_TOL
+            st = robot.status()
+            assert (st & sp.capi.STATUS_UNHANDLED).sum() == 0
+            assert ((st & sp.capi.STATUS_SINGULAR_PATH) != 0)[m[name + "_singular"]].all()
+            assert rel_err(tau, m[name + "_tau"][k]).max() < REL_TOL
 
 
 @pytest.mark.gpu
