@@ -550,7 +550,8 @@ int osc_finalize_controller(osc_handle* h, int use_previous_torques) {
 						"task cannot be added to the controller because it is in the nullspace of a full joint task");
 		if (h->tasks[i].type == OSC_TASK_JOINT && h->prog.jt[h->tasks[i].index].k == h->model.n) closed = true;
 	}
-	// hierarchy signatures with a compiled kernel: [JT full], [MFT], [MFT, JT full]
+	// hierarchy signatures with a specialised fast kernel: [JT full], [MFT], [MFT, JT full]; anything else runs on the
+	// general-hierarchy kernel
 	int R = 0;
 	bool jt = false;
 	bool ok = true;
@@ -568,10 +569,12 @@ int osc_finalize_controller(osc_handle* h, int use_previous_torques) {
 	} else {
 		ok = false;
 	}
-	if (!ok || !osc::cycle_signature_available(h->model.n, R, jt))
-		return fail(h, OSC_ERR_UNSUPPORTED,
-					"task hierarchy not supported by this build: supported are [full JointTask], [MotionForceTask], "
-					"[MotionForceTask, full JointTask]");
+	if (!ok) {  // partial joint tasks, several motion-force tasks, ...: the general-hierarchy kernel
+		R = -1;
+		jt = false;
+	}
+	if (!osc::cycle_signature_available(h->model.n, R, jt))
+		return fail(h, OSC_ERR_UNSUPPORTED, "no kernel compiled for this robot dof (see OSC_CYCLE_DOFS in csrc/osc_launch.h)");
 	h->sig_R = R;
 	h->sig_jt = jt;
 	h->prog.use_prev_torques = use_previous_torques ? 1 : 0;

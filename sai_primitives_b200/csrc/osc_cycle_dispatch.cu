@@ -6,7 +6,8 @@ OSC_CYCLE_DOFS(DECL)
 #undef DECL
 
 bool cycle_signature_available(int n, int R, bool has_jt) {
-	if (R < 0 || R > 6 || R > n) return false;
+	if (R > 6 || R > n) return false;
+	if (R < 0) R = 1;  // general-hierarchy kernel: only the dof has to be compiled in
 	if (R == 0 && !has_jt) return false;
 #define CHECK(m) \
 	if (n == m) return true;

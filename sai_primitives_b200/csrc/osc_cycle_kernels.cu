@@ -23,7 +23,7 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 		// the SVD path for the robots the fast kernel handed over (usually none or few: exits immediately)
 		const long long want = (P.n_robots + 63) / 64;
 		const unsigned sgrid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
-		osc_singular_kernel<N, R, JT><<<sgrid, 64, 0, stream>>>(P);
+		osc_singular_kernel<N><<<sgrid, 64, 0, stream>>>(P);
 	}
 	return cudaGetLastError();
 }
@@ -41,11 +41,19 @@ static cudaError_t launch_rank(bool has_jt, const OscProgram& P, cudaStream_t st
 	}
 }
 
+template <int N>
+static cudaError_t launch_generic(const OscProgram& P, cudaStream_t stream) {
+	const unsigned grid = (unsigned)((P.n_robots + 63) / 64);
+	osc_generic_kernel<N><<<grid, 64, 0, stream>>>(P);
+	return cudaGetLastError();
+}
+
 #define CONCAT_(a, b) a##b
 #define CONCAT(a, b) CONCAT_(a, b)
 
 cudaError_t CONCAT(launch_cycle_n, OSC_INST_N)(int R, bool has_jt, const OscProgram& P, cudaStream_t stream) {
 	constexpr int N = OSC_INST_N;
+	if (R < 0) return launch_generic<N>(P, stream);	 // general hierarchy: every robot on the general path
 	switch (R) {
 		case 0:
 			if constexpr (OSC_ONLY_R != 0) return cudaErrorNotSupported;

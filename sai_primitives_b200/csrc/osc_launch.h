@@ -14,8 +14,9 @@ constexpr int kCycleBlock = OSC_CYCLE_BLOCK;
 // robot dofs the fused cycle kernel is instantiated for (one translation unit each, see Makefile)
 #define OSC_CYCLE_DOFS(X) X(4) X(6) X(7) X(8)
 
-// Fused control cycle for hierarchy signature (n, R, has_jt); cudaErrorNotSupported when the
-// signature is not compiled in (see osc_cycle_inst.inc).
+// Fused control cycle for hierarchy signature (n, R, has_jt): R = rank of a leading MotionForceTask (0: none),
+// has_jt = a full JointTask closes the hierarchy; R < 0 selects the general-hierarchy kernel.
+// cudaErrorNotSupported when the dof is not compiled in (OSC_CYCLE_DOFS).
 cudaError_t launch_cycle(int n, int R, bool has_jt, const OscProgram& P, cudaStream_t stream);
 bool cycle_signature_available(int n, int R, bool has_jt);
 

@@ -192,20 +192,15 @@ static __device__ __noinline__ void lambda_of(const double* J, int r, int n, con
 
 }  // namespace sg
 
-// One full control cycle for the robots in `list` (count on the device).  Signature as the fast kernel:
-// a leading MotionForceTask of rank R (first in the hierarchy, N_prec = I) and optionally a full JointTask.
-template <int N, int R, bool HAS_JT>
-static __device__ __noinline__ void singular_cycle_one(const OscProgram& P, const int64_t i) {
+// One full control cycle of ONE robot for an arbitrary task hierarchy (P.tasks), following the reference's
+// RobotController loop (src/RobotController.cpp:68-118) with explicit N_prec chaining.  The task models are pure
+// functions of the state, so model update and torque of task k are evaluated together, in hierarchy order.
+template <int N>
+static __device__ __noinline__ void generic_cycle_one(const OscProgram& P, const int64_t i, uint32_t status) {
 	using namespace sg;
 	const int64_t NR = P.n_robots;
 	const DevModel& mdl = P.model;
-	const DevMft& t = P.mft[0];
-	const osc_mft_params& p = t.p;
-	double* st = t.st;
-	int32_t* ist = t.ist;
 	constexpr int n = N;
-	constexpr int r = R;
-	uint32_t status = OSC_STATUS_SINGULAR_PATH;
 
 	double q[N], dq[N];
 	for (int j = 0; j < N; j++) {
@@ -220,320 +215,343 @@ static __device__ __noinline__ void singular_cycle_one(const OscProgram& P, cons
 		for (int b = 0; b < N; b++) M[a * N + b] = kd.M[a][b];
 	spd_inverse(M, n, Minv);
 
-	// _jacobian = P * JWorldFrame (MotionForceTask.cpp:261-263); N_prec = I so _projected_jacobian = _jacobian
-	double x[3], Rc[9];
-	frame_pose<N>(kd, t.body, t.ctrl_R, t.ctrl_t, x, Rc);
-	double JT0[N][6];
-	point_jacobian_t<N>(mdl, kd, t.body, x, JT0);
-	double J[6 * N];
-	for (int j = 0; j < N; j++) {
-		double v[3] = {JT0[j][0], JT0[j][1], JT0[j][2]}, w[3] = {JT0[j][3], JT0[j][4], JT0[j][5]};
-		if (!t.full) {
-			double tv[3], tw[3];
-			mat3_vec(t.Pt, v, tv);
-			mat3_vec(t.Pr, w, tw);
-			for (int k = 0; k < 3; k++) {
-				v[k] = tv[k];
-				w[k] = tw[k];
-			}
-		}
-		for (int k = 0; k < 3; k++) {
-			J[k * N + j] = v[k];
-			J[(3 + k) * N + j] = w[k];
-		}
-	}
-
-	// ---- SingularityHandler::updateTaskModel (:75-228)
-	constexpr int K = (N < 6) ? N : 6;	// thin SVD width
-	double U[6 * K], sv[K], V[N * K];
-	svd_thin(J, 6, n, U, sv, V);
-	int n_ns = 0, n_s = 0;	// columns of the non-singular / singular task range
-	double alpha = 1.0;
-	if (sv[0] < p.s_abs_tol) {	// fully singular (:83-98)
-		alpha = 0.0;
-		n_ns = 0;
-		n_s = r;
-	} else if (r == 1) {  // Appendix C6
-		n_ns = 1;
-	} else {
-		n_ns = r;
-		for (int c = 1; c < r; c++) {
-			const double icn = sv[c] / sv[0];
-			if (icn < p.s_max) {
-				alpha = fmin(fmax((icn - p.s_min) / (p.s_max - p.s_min), 0.0), 1.0);
-				n_ns = c;
-				n_s = r - c;
-				break;
-			}
-		}
-	}
-	// U_ns = U[:, :n_ns], U_s = U[:, n_ns:n_ns+n_s], V_s likewise; J_ns = U_ns^T J, J_s = U_s^T J
-	double Uns[6 * 6], Us[6 * 6], Vs[N * 6], Jns[6 * N], Js[6 * N];
-	for (int a = 0; a < 6; a++) {
-		for (int c = 0; c < n_ns; c++) Uns[a * n_ns + c] = U[a * K + c];
-		for (int c = 0; c < n_s; c++) Us[a * n_s + c] = U[a * K + n_ns + c];
-	}
-	for (int a = 0; a < N; a++)
-		for (int c = 0; c < n_s; c++) Vs[a * n_s + c] = V[a * K + n_ns + c];
-	double Lns[36], Nns[N * N], Ls[36], Nmat[N * N], Ljs[36], Jpost[6 * N];
-	for (int a = 0; a < N * N; a++) Nns[a] = ((a / N) == (a % N)) ? 1.0 : 0.0;
-	if (n_ns > 0) {
-		mm_at(Uns, 6, n_ns, J, n, Jns);
-		op_space(Jns, n_ns, n, Minv, Lns, Nns);
-	}
-	if (n_s > 0 && n_ns > 0) {
-		mm_at(Us, 6, n_s, J, n, Js);
-		lambda_of(Js, n_s, n, Minv, Ls);
-	}
-	const bool handling = p.singularity_handling_enabled != 0;
-	bool have_post = false;
-	if (n_s == 0 || !handling) {
-		for (int a = 0; a < N * N; a++) Nmat[a] = Nns[a];
-	} else if (n_ns == 0) {
-		for (int a = 0; a < N * N; a++) Nmat[a] = ((a / N) == (a % N)) ? 1.0 : 0.0;	 // N = N_prec = I
-	} else {
-		double Njs[N * N];
-		mm_at(Vs, n, n_s, Nns, n, Jpost);  // V_s^T N_ns (N_prec = I)
-		op_space(Jpost, n_s, n, Minv, Ljs, Njs);
-		mm(Njs, n, n, Nns, n, Nmat);
-		have_post = true;
-	}
-	// decoupling (:160-225)
-	double Lns_mod[36], Ls_mod[36], Ljs_mod[36];
-	double Mbinv[N * N];
-	if (p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES) {
-		double Mb[N * N];
-		for (int a = 0; a < N * N; a++) Mb[a] = M[a];
-		for (int a = 0; a < N; a++)
-			if (Mb[a * N + a] < p.bie_threshold) Mb[a * N + a] = p.bie_threshold;
-		spd_inverse(Mb, n, Mbinv);
-		if (n_ns > 0) lambda_of(Jns, n_ns, n, Mbinv, Lns_mod);
-		if (n_s > 0 && n_ns > 0) lambda_of(Js, n_s, n, Mbinv, Ls_mod);
-		if (have_post) lambda_of(Jpost, n_s, n, Mbinv, Ljs_mod);
-	} else if (p.dynamic_decoupling_type == OSC_FULL_DYNAMIC_DECOUPLING) {
-		for (int a = 0; a < n_ns * n_ns; a++) Lns_mod[a] = Lns[a];
-		for (int a = 0; a < n_s * n_s; a++) Ls_mod[a] = Ls[a];
-		for (int a = 0; a < n_s * n_s; a++) Ljs_mod[a] = Ljs[a];
-	} else {
-		for (int a = 0; a < 36; a++) {
-			Lns_mod[a] = 0.0;
-			Ls_mod[a] = 0.0;
-			Ljs_mod[a] = 0.0;
-		}
-		for (int a = 0; a < n_ns; a++) Lns_mod[a * n_ns + a] = 1.0;
-		for (int a = 0; a < n_s; a++) {
-			Ls_mod[a * n_s + a] = 1.0;
-			Ljs_mod[a * n_s + a] = 1.0;
-		}
-	}
-
-	// ---- classifySingularity (:230-295)
-	int32_t c1 = ist[(int64_t)MI_T1_COUNTER * NR + i], c2 = ist[(int64_t)MI_T2_COUNTER * NR + i];
-	int32_t n_types_prev = ist[(int64_t)MI_N_TYPES * NR + i];
-	int32_t hist_head = ist[(int64_t)MI_HIST_HEAD * NR + i], hist_size = ist[(int64_t)MI_HIST_SIZE * NR + i];
-	double q_prior[N], dq_prior[N];
-	const bool upd = P.update_models != 0;
-	if (upd && (n_types_prev == 0 || c2 > c1)) {
-		for (int j = 0; j < N; j++) {
-			q_prior[j] = q[j];
-			dq_prior[j] = dq[j];
-			st[(int64_t)(MC_Q_PRIOR + j) * NR + i] = q[j];
-			st[(int64_t)(MC_DQ_PRIOR + j) * NR + i] = dq[j];
-		}
-	} else {
-		for (int j = 0; j < N; j++) q_prior[j] = st[(int64_t)(MC_Q_PRIOR + j) * NR + i];
-	}
-	int n_types = 0;
-	bool any_type1 = false;
-	if (n_s == 0) {
-		if (upd) {
-			c1 = c2 = 0;
-			hist_head = hist_size = 0;
-		}
-	} else {
-		n_types = n_s;
-		for (int c = 0; c < n_s; c++) {
-			double qq[N];
-			for (int j = 0; j < N; j++) qq[j] = q[j] + p.perturb_step_size * Vs[j * n_s + c];
-			KinDyn<N> kp;
-			forward_kinematics<N>(mdl, qq, kp);
-			double xp[3], Rp[9], dphi[3];
-			frame_pose<N>(kp, t.body, t.ctrl_R, t.ctrl_t, xp, Rp);
-			orientation_error(Rp, Rc, dphi);
-			double mot = 0.0;
-			for (int k = 0; k < 3; k++) mot += (xp[k] - x[k]) * Us[k * n_s + c] + dphi[k] * Us[(3 + k) * n_s + c];
-			if (fabs(mot) > p.type_1_tol) any_type1 = true;
-		}
-		if (upd) {
-			const int pos = (hist_head + hist_size) % OSC_HIST_MAX;
-			int32_t* word = &ist[(int64_t)(MI_HIST_BITS + pos / 32) * NR + i];
-			if (any_type1) {
-				*word |= (1 << (pos % 32));
-				c1++;
-			} else {
-				*word &= ~(1 << (pos % 32));
-				c2++;
-			}
-			hist_size++;
-			if (hist_size > p.buffer_size) {
-				const int32_t w0 = ist[(int64_t)(MI_HIST_BITS + hist_head / 32) * NR + i];
-				if ((w0 >> (hist_head % 32)) & 1)
-					c1--;
-				else
-					c2--;
-				hist_head = (hist_head + 1) % OSC_HIST_MAX;
-				hist_size--;
-			}
-		}
-	}
-	if (upd) {
-		ist[(int64_t)MI_T1_COUNTER * NR + i] = c1;
-		ist[(int64_t)MI_T2_COUNTER * NR + i] = c2;
-		ist[(int64_t)MI_N_TYPES * NR + i] = n_types;
-		ist[(int64_t)MI_HIST_HEAD * NR + i] = hist_head;
-		ist[(int64_t)MI_HIST_SIZE * NR + i] = hist_size;
-	} else {
-		n_types = n_types_prev;
-	}
-
-	// ---- MotionForceTask::computeTorques (:278-509) + SingularityHandler::computeTorques (:297-368)
-	double fstar[6], F[6];
-	mft_control_law<N>(t, NR, i, x, Rc, JT0, dq, P.write_observers != 0, fstar, F, status);
+	double Nprec[N * N];
+	for (int a = 0; a < N * N; a++) Nprec[a] = ((a / N) == (a % N)) ? 1.0 : 0.0;
 	double tau[N];
 	for (int j = 0; j < N; j++) tau[j] = 0.0;
-	{
-		double a[6], b[6], c[6];
-		if (n_ns > 0) {
-			mv_t(Uns, 6, n_ns, fstar, a);  // U_ns^T f*
-			mv_t(Uns, 6, n_ns, F, b);
-			const bool plain = (n_types != 0) && (p.dynamic_decoupling_type == OSC_IMPEDANCE);
-			if (plain) {
-				for (int k = 0; k < n_ns; k++) c[k] = a[k] + b[k];
-			} else {
-				mv(Lns_mod, n_ns, n_ns, a, c);
-				for (int k = 0; k < n_ns; k++) c[k] += b[k];
-			}
-			mv_t(Jns, n_ns, n, c, tau);	 // tau_ns
-		}
-		const bool blended = (n_types != 0) && (p.dynamic_decoupling_type != OSC_IMPEDANCE) && n_ns > 0 && handling && n_s > 0;
-		if (blended) {
-			double js[N], u[N], vt[6], tmp[6];
-			if (c1 > c2 || p.enforce_type_1_strategy) {
-				status |= OSC_STATUS_TYPE1;
-				for (int j = 0; j < N; j++) u[j] = -p.kp_type_1 * (q[j] - q_prior[j]) - p.kv_type_1 * dq[j];
-				mv_t(Vs, n, n_s, u, vt);
-				mv(Ljs_mod, n_s, n_s, vt, tmp);
-				mv_t(Jpost, n_s, n, tmp, js);
-			} else {
-				status |= OSC_STATUS_TYPE2;
-				double dir[N];
-				for (int j = 0; j < N; j++) {
-					dir[j] = st[(int64_t)(MC_TYPE2_DIR + j) * NR + i];
-					if (Vs[j * n_s + 0] != 0.0) {
-						if (fabs(q[j] - mdl.q_upper[j]) < p.type_2_angle_threshold)
-							dir[j] = -1.0;
-						else if (fabs(q[j] - mdl.q_lower[j]) < p.type_2_angle_threshold)
-							dir[j] = 1.0;
-					}
-					st[(int64_t)(MC_TYPE2_DIR + j) * NR + i] = dir[j];
-				}
-				double ff[6], nf = 0.0, fTd = 0.0;
-				for (int k = 0; k < 6; k++) {
-					ff[k] = fstar[k] + F[k];
-					nf += ff[k] * ff[k];
-				}
-				nf = sqrt(nf);
-				for (int k = 0; k < 6; k++) fTd += (nf > 0.0 ? ff[k] / nf : ff[k]) * Us[k * n_s + 0];
-				for (int j = 0; j < N; j++) u[j] = dir[j] * fabs(fTd) * p.type_2_torque_ratio * mdl.effort[j];
-				double js2[N];
-				mv_t(Vs, n, n_s, u, vt);
-				mv_t(Jpost, n_s, n, vt, js);
-				for (int j = 0; j < N; j++) u[j] = -p.kv_type_2 * dq[j];
-				mv_t(Vs, n, n_s, u, vt);
-				mv(Ljs_mod, n_s, n_s, vt, tmp);
-				mv_t(Jpost, n_s, n, tmp, js2);
-				for (int j = 0; j < N; j++) js[j] += js2[j];
-			}
-			double ts[N];
-			mv_t(Us, 6, n_s, fstar, a);
-			mv_t(Us, 6, n_s, F, b);
-			mv(Ls_mod, n_s, n_s, a, c);
-			for (int k = 0; k < n_s; k++) c[k] += b[k];
-			mv_t(Js, n_s, n, c, ts);
-			for (int j = 0; j < N; j++) {
-				if (isnan(ts[j])) {
-					ts[j] = 0.0;
-					status |= OSC_STATUS_NAN_SCRUBBED;
-				} else if (ts[j] > mdl.effort[j])
-					ts[j] = mdl.effort[j];
-				else if (ts[j] < -mdl.effort[j])
-					ts[j] = -mdl.effort[j];
-				tau[j] += alpha * ts[j] + (1.0 - alpha) * js[j];
-			}
-		}
-	}
 
-	// ---- JointTask with N_prec = N (JointTask.cpp:218-356), S = I
-	if constexpr (HAS_JT) {
-		const DevJt& jt = P.jt[0];
-		const osc_joint_params& jp = jt.p;
-		// range basis of J_proj = N_prec: thin SVD, relative tolerance 1e-3 (SaiModel::matrixRangeBasis)
-		double Ur[N * N], sr[N], Vr[N * N];
-		int kr = 0;
-		const double nn = sqrt(fro2(Nmat, N * N));
-		if (nn >= 1e-3) {
-			svd_thin(Nmat, n, n, Ur, sr, Vr);
-			if (sr[0] >= 1e-3) {
-				kr = n;
-				for (int c = n - 1; c > 0; c--) {
-					if (sr[c] / sr[0] < 1e-3)
-						kr--;
-					else
-						break;
+	for (int task = 0; task < P.n_tasks; task++) {
+		double Nmat[N * N];	 // null space of this task (getTaskNullspace)
+		if (P.tasks[task].type == OSC_TASK_MOTION_FORCE) {
+			const DevMft& t = P.mft[P.tasks[task].index];
+			const osc_mft_params& p = t.p;
+			double* st = t.st;
+			int32_t* ist = t.ist;
+			const int r = t.rank;
+			// _jacobian = P * JWorldFrame, _projected_jacobian = _jacobian * N_prec (MotionForceTask.cpp:261-264)
+			double x[3], Rc[9];
+			frame_pose<N>(kd, t.body, t.ctrl_R, t.ctrl_t, x, Rc);
+			double JT0[N][6];
+			point_jacobian_t<N>(mdl, kd, t.body, x, JT0);
+			double J0[6 * N], J[6 * N];
+			for (int j = 0; j < N; j++) {
+				double v[3] = {JT0[j][0], JT0[j][1], JT0[j][2]}, w[3] = {JT0[j][3], JT0[j][4], JT0[j][5]};
+				if (!t.full) {
+					double tv[3], tw[3];
+					mat3_vec(t.Pt, v, tv);
+					mat3_vec(t.Pr, w, tw);
+					for (int k = 0; k < 3; k++) {
+						v[k] = tv[k];
+						w[k] = tw[k];
+					}
+				}
+				for (int k = 0; k < 3; k++) {
+					J0[k * N + j] = v[k];
+					J0[(3 + k) * N + j] = w[k];
 				}
 			}
-		}
-		if (kr == 0) {
-			status |= OSC_STATUS_ZERO_RANGE;
-		} else {
-			double Ub[N * N];  // n x kr, identity when the range is the whole space
+			mm(J0, 6, n, Nprec, n, J);
+
+			// ---- SingularityHandler::updateTaskModel (:75-228)
+			constexpr int K = (N < 6) ? N : 6;	// thin SVD width
+			double U[6 * K], sv[K], V[N * K];
+			svd_thin(J, 6, n, U, sv, V);
+			int n_ns = 0, n_s = 0;	// columns of the non-singular / singular task range
+			double alpha = 1.0;
+			if (sv[0] < p.s_abs_tol) {	// fully singular (:83-98)
+				alpha = 0.0;
+				n_ns = 0;
+				n_s = r;
+			} else if (r == 1) {
+				n_ns = 1;
+			} else {
+				n_ns = r;
+				for (int c = 1; c < r; c++) {
+					const double icn = sv[c] / sv[0];
+					if (icn < p.s_max) {
+						alpha = fmin(fmax((icn - p.s_min) / (p.s_max - p.s_min), 0.0), 1.0);
+						n_ns = c;
+						n_s = r - c;
+						break;
+					}
+				}
+			}
+			if (n_s > 0) status |= OSC_STATUS_SINGULAR_PATH;
+			double Uns[6 * 6], Us[6 * 6], Vs[N * 6], Jns[6 * N], Js[6 * N];
+			for (int a = 0; a < 6; a++) {
+				for (int c = 0; c < n_ns; c++) Uns[a * n_ns + c] = U[a * K + c];
+				for (int c = 0; c < n_s; c++) Us[a * n_s + c] = U[a * K + n_ns + c];
+			}
 			for (int a = 0; a < N; a++)
-				for (int c = 0; c < kr; c++) Ub[a * kr + c] = (kr == n) ? ((a == c) ? 1.0 : 0.0) : Ur[a * N + c];
-			double Jr[N * N], Mp[N * N], Nj[N * N], Mmod[N * N];
-			mm_at(Ub, n, kr, Nmat, n, Jr);	// U^T J_proj  (kr x n)
-			op_space(Jr, kr, n, Minv, Mp, Nj);
-			if (jp.dynamic_decoupling_type == OSC_FULL_DYNAMIC_DECOUPLING) {
-				for (int a = 0; a < kr * kr; a++) Mmod[a] = Mp[a];
-			} else if (jp.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES) {
-				double Mb[N * N], Mbi[N * N];
+				for (int c = 0; c < n_s; c++) Vs[a * n_s + c] = V[a * K + n_ns + c];
+			double Lns[36], Nns[N * N], Ls[36], Ljs[36], Jpost[6 * N];
+			for (int a = 0; a < N * N; a++) Nns[a] = ((a / N) == (a % N)) ? 1.0 : 0.0;
+			if (n_ns > 0) {
+				mm_at(Uns, 6, n_ns, J, n, Jns);
+				op_space(Jns, n_ns, n, Minv, Lns, Nns);
+			}
+			if (n_s > 0 && n_ns > 0) {
+				mm_at(Us, 6, n_s, J, n, Js);
+				lambda_of(Js, n_s, n, Minv, Ls);
+			}
+			const bool handling = p.singularity_handling_enabled != 0;
+			bool have_post = false;
+			if (n_s == 0 || !handling) {
+				for (int a = 0; a < N * N; a++) Nmat[a] = Nns[a];
+			} else if (n_ns == 0) {
+				for (int a = 0; a < N * N; a++) Nmat[a] = Nprec[a];	 // fully singular: pass the task through (:149-151)
+			} else {
+				double Njs[N * N], T1[6 * N];
+				mm_at(Vs, n, n_s, Nns, n, T1);	   // V_s^T N_ns
+				mm(T1, n_s, n, Nprec, n, Jpost);  // ... N_prec
+				op_space(Jpost, n_s, n, Minv, Ljs, Njs);
+				mm(Njs, n, n, Nns, n, Nmat);
+				have_post = true;
+			}
+			// decoupling (:160-225)
+			double Lns_mod[36], Ls_mod[36], Ljs_mod[36];
+			if (p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES) {
+				double Mb[N * N], Mbinv[N * N];
 				for (int a = 0; a < N * N; a++) Mb[a] = M[a];
 				for (int a = 0; a < N; a++)
-					if (Mb[a * N + a] < jp.bie_threshold) Mb[a * N + a] = jp.bie_threshold;
-				spd_inverse(Mb, n, Mbi);
-				lambda_of(Jr, kr, n, Mbi, Mmod);
+					if (Mb[a * N + a] < p.bie_threshold) Mb[a * N + a] = p.bie_threshold;
+				spd_inverse(Mb, n, Mbinv);
+				if (n_ns > 0) lambda_of(Jns, n_ns, n, Mbinv, Lns_mod);
+				if (n_s > 0 && n_ns > 0) lambda_of(Js, n_s, n, Mbinv, Ls_mod);
+				if (have_post) lambda_of(Jpost, n_s, n, Mbinv, Ljs_mod);
+			} else if (p.dynamic_decoupling_type == OSC_FULL_DYNAMIC_DECOUPLING) {
+				for (int a = 0; a < n_ns * n_ns; a++) Lns_mod[a] = Lns[a];
+				for (int a = 0; a < n_s * n_s; a++) Ls_mod[a] = Ls[a];
+				for (int a = 0; a < n_s * n_s; a++) Ljs_mod[a] = Ljs[a];
 			} else {
-				for (int a = 0; a < kr * kr; a++) Mmod[a] = ((a / kr) == (a % kr)) ? 1.0 : 0.0;
+				for (int a = 0; a < 36; a++) {
+					Lns_mod[a] = 0.0;
+					Ls_mod[a] = 0.0;
+					Ljs_mod[a] = 0.0;
+				}
+				for (int a = 0; a < n_ns; a++) Lns_mod[a * n_ns + a] = 1.0;
+				for (int a = 0; a < n_s; a++) {
+					Ls_mod[a * n_s + a] = 1.0;
+					Ljs_mod[a * n_s + a] = 1.0;
+				}
 			}
-			double pid[N], acc[N];
-			joint_control_law<N, N>(jt, NR, i, q, dq, pid, acc);
-			double a1[N], a2[N], f[N], g[N];
-			mv_t(Ub, n, kr, acc, a1);
-			mv(Mp, kr, kr, a1, f);
-			mv_t(Ub, n, kr, pid, a2);
-			mv(Mmod, kr, kr, a2, g);
-			for (int k = 0; k < kr; k++) f[k] += g[k];
-			if (P.use_prev_torques) {  // - J_proj^T U M_partial U^T S Minv tau_prec
-				double mt[N], ut[N], w[N];
-				mv(Minv, n, n, tau, mt);
-				mv_t(Ub, n, kr, mt, ut);
-				mv(Mp, kr, kr, ut, w);
-				for (int k = 0; k < kr; k++) f[k] -= w[k];
+
+			// ---- classifySingularity (:230-295)
+			int32_t c1 = ist[(int64_t)MI_T1_COUNTER * NR + i], c2 = ist[(int64_t)MI_T2_COUNTER * NR + i];
+			const int32_t n_types_prev = ist[(int64_t)MI_N_TYPES * NR + i];
+			int32_t hist_head = ist[(int64_t)MI_HIST_HEAD * NR + i], hist_size = ist[(int64_t)MI_HIST_SIZE * NR + i];
+			double q_prior[N];
+			const bool upd = P.update_models != 0;
+			if (upd && (n_types_prev == 0 || c2 > c1)) {
+				for (int j = 0; j < N; j++) {
+					q_prior[j] = q[j];
+					st[(int64_t)(MC_Q_PRIOR + j) * NR + i] = q[j];
+					st[(int64_t)(MC_DQ_PRIOR + j) * NR + i] = dq[j];
+				}
+			} else {
+				for (int j = 0; j < N; j++) q_prior[j] = st[(int64_t)(MC_Q_PRIOR + j) * NR + i];
 			}
-			double uf[N], tj[N];
-			mv(Ub, n, kr, f, uf);
-			mv_t(Nmat, n, n, uf, tj);
-			for (int j = 0; j < N; j++) tau[j] += tj[j];
+			int n_types = 0;
+			bool any_type1 = false;
+			if (n_s == 0) {
+				if (upd) {
+					c1 = c2 = 0;
+					hist_head = hist_size = 0;
+				}
+			} else {
+				n_types = n_s;
+				for (int c = 0; c < n_s; c++) {
+					double qq[N];
+					for (int j = 0; j < N; j++) qq[j] = q[j] + p.perturb_step_size * Vs[j * n_s + c];
+					KinDyn<N> kp;
+					forward_kinematics<N>(mdl, qq, kp);
+					double xp[3], Rp[9], dphi[3];
+					frame_pose<N>(kp, t.body, t.ctrl_R, t.ctrl_t, xp, Rp);
+					orientation_error(Rp, Rc, dphi);
+					double mot = 0.0;
+					for (int k = 0; k < 3; k++) mot += (xp[k] - x[k]) * Us[k * n_s + c] + dphi[k] * Us[(3 + k) * n_s + c];
+					if (fabs(mot) > p.type_1_tol) any_type1 = true;
+				}
+				if (upd) {
+					const int pos = (hist_head + hist_size) % OSC_HIST_MAX;
+					uint32_t* word = reinterpret_cast<uint32_t*>(&ist[(int64_t)(MI_HIST_BITS + pos / 32) * NR + i]);
+					if (any_type1) {
+						*word |= (1u << (pos % 32));
+						c1++;
+					} else {
+						*word &= ~(1u << (pos % 32));
+						c2++;
+					}
+					hist_size++;
+					if (hist_size > p.buffer_size) {
+						const uint32_t w0 = (uint32_t)ist[(int64_t)(MI_HIST_BITS + hist_head / 32) * NR + i];
+						if ((w0 >> (hist_head % 32)) & 1u)
+							c1--;
+						else
+							c2--;
+						hist_head = (hist_head + 1) % OSC_HIST_MAX;
+						hist_size--;
+					}
+				}
+			}
+			if (upd) {
+				ist[(int64_t)MI_T1_COUNTER * NR + i] = c1;
+				ist[(int64_t)MI_T2_COUNTER * NR + i] = c2;
+				ist[(int64_t)MI_N_TYPES * NR + i] = n_types;
+				ist[(int64_t)MI_HIST_HEAD * NR + i] = hist_head;
+				ist[(int64_t)MI_HIST_SIZE * NR + i] = hist_size;
+			} else {
+				n_types = n_types_prev;
+			}
+
+			// ---- MotionForceTask::computeTorques (:278-509) + SingularityHandler::computeTorques (:297-368)
+			double fstar[6], F[6];
+			mft_control_law<N>(t, NR, i, x, Rc, JT0, dq, P.write_observers != 0, fstar, F, status);
+			double tt[N];
+			for (int j = 0; j < N; j++) tt[j] = 0.0;
+			double a[6], b[6], c[6];
+			if (n_ns > 0) {
+				mv_t(Uns, 6, n_ns, fstar, a);  // U_ns^T f*
+				mv_t(Uns, 6, n_ns, F, b);
+				const bool plain = (n_types != 0) && (p.dynamic_decoupling_type == OSC_IMPEDANCE);
+				if (plain) {
+					for (int k = 0; k < n_ns; k++) c[k] = a[k] + b[k];
+				} else {
+					mv(Lns_mod, n_ns, n_ns, a, c);
+					for (int k = 0; k < n_ns; k++) c[k] += b[k];
+				}
+				mv_t(Jns, n_ns, n, c, tt);	// tau_ns
+			}
+			const bool blended = (n_types != 0) && (p.dynamic_decoupling_type != OSC_IMPEDANCE) && n_ns > 0 && handling && n_s > 0;
+			if (blended) {
+				double js[N], u[N], vt[6], tmp[6];
+				if (c1 > c2 || p.enforce_type_1_strategy) {
+					status |= OSC_STATUS_TYPE1;
+					for (int j = 0; j < N; j++) u[j] = -p.kp_type_1 * (q[j] - q_prior[j]) - p.kv_type_1 * dq[j];
+					mv_t(Vs, n, n_s, u, vt);
+					mv(Ljs_mod, n_s, n_s, vt, tmp);
+					mv_t(Jpost, n_s, n, tmp, js);
+				} else {
+					status |= OSC_STATUS_TYPE2;
+					double dir[N];
+					for (int j = 0; j < N; j++) {
+						dir[j] = st[(int64_t)(MC_TYPE2_DIR + j) * NR + i];
+						if (Vs[j * n_s + 0] != 0.0) {
+							if (fabs(q[j] - mdl.q_upper[j]) < p.type_2_angle_threshold)
+								dir[j] = -1.0;
+							else if (fabs(q[j] - mdl.q_lower[j]) < p.type_2_angle_threshold)
+								dir[j] = 1.0;
+						}
+						st[(int64_t)(MC_TYPE2_DIR + j) * NR + i] = dir[j];
+					}
+					double ff[6], nf = 0.0, fTd = 0.0;
+					for (int k = 0; k < 6; k++) {
+						ff[k] = fstar[k] + F[k];
+						nf += ff[k] * ff[k];
+					}
+					nf = sqrt(nf);
+					for (int k = 0; k < 6; k++) fTd += (nf > 0.0 ? ff[k] / nf : ff[k]) * Us[k * n_s + 0];
+					for (int j = 0; j < N; j++) u[j] = dir[j] * fabs(fTd) * p.type_2_torque_ratio * mdl.effort[j];
+					double js2[N];
+					mv_t(Vs, n, n_s, u, vt);
+					mv_t(Jpost, n_s, n, vt, js);
+					for (int j = 0; j < N; j++) u[j] = -p.kv_type_2 * dq[j];
+					mv_t(Vs, n, n_s, u, vt);
+					mv(Ljs_mod, n_s, n_s, vt, tmp);
+					mv_t(Jpost, n_s, n, tmp, js2);
+					for (int j = 0; j < N; j++) js[j] += js2[j];
+				}
+				double ts[N];
+				mv_t(Us, 6, n_s, fstar, a);
+				mv_t(Us, 6, n_s, F, b);
+				mv(Ls_mod, n_s, n_s, a, c);
+				for (int k = 0; k < n_s; k++) c[k] += b[k];
+				mv_t(Js, n_s, n, c, ts);
+				for (int j = 0; j < N; j++) {
+					if (isnan(ts[j])) {
+						ts[j] = 0.0;
+						status |= OSC_STATUS_NAN_SCRUBBED;
+					} else if (ts[j] > mdl.effort[j])
+						ts[j] = mdl.effort[j];
+					else if (ts[j] < -mdl.effort[j])
+						ts[j] = -mdl.effort[j];
+					tt[j] += alpha * ts[j] + (1.0 - alpha) * js[j];
+				}
+			}
+			// computeTorques(tau_prec) subtracts a term that is identically zero (MotionForceTask::_Lambda == 0, Appendix C1)
+			for (int j = 0; j < N; j++) tau[j] += tt[j];
+		} else {
+			// ---- JointTask::updateTaskModel / computeTorques with a general N_prec and selection S (JointTask.cpp:218-356)
+			const DevJt& jt = P.jt[P.tasks[task].index];
+			const osc_joint_params& jp = jt.p;
+			const int k = jt.k;
+			double S[N * N], Jp[N * N];
+			for (int a = 0; a < k; a++)
+				for (int j = 0; j < N; j++) S[a * N + j] = jt.S[a][j];
+			mm(S, k, n, Nprec, n, Jp);	// _projected_jacobian (k x n)
+			// range basis (SaiModel::matrixRangeBasis, tolerance 1e-3)
+			double Ur[N * N], sr[N], Vr[N * N];
+			int kr = 0;
+			if (sqrt(fro2(Jp, k * n)) >= 1e-3) {
+				svd_thin(Jp, k, n, Ur, sr, Vr);	 // Ur: k x min(k,n) = k x k
+				if (sr[0] >= 1e-3) {
+					kr = k;
+					for (int c = k - 1; c > 0; c--) {
+						if (sr[c] / sr[0] < 1e-3)
+							kr--;
+						else
+							break;
+					}
+				}
+			}
+			if (kr == 0) {
+				status |= OSC_STATUS_ZERO_RANGE;
+				for (int a = 0; a < N * N; a++) Nmat[a] = ((a / N) == (a % N)) ? 1.0 : 0.0;
+			} else {
+				double Ub[N * N];  // k x kr, identity when the range is the whole task space
+				for (int a = 0; a < k; a++)
+					for (int c = 0; c < kr; c++) Ub[a * kr + c] = (kr == k) ? ((a == c) ? 1.0 : 0.0) : Ur[a * k + c];
+				double Jr[N * N], Mp[N * N], Mmod[N * N];
+				mm_at(Ub, k, kr, Jp, n, Jr);  // U^T J_proj  (kr x n)
+				op_space(Jr, kr, n, Minv, Mp, Nmat);
+				if (jp.dynamic_decoupling_type == OSC_FULL_DYNAMIC_DECOUPLING) {
+					for (int a = 0; a < kr * kr; a++) Mmod[a] = Mp[a];
+				} else if (jp.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES) {
+					double Mb[N * N], Mbi[N * N];
+					for (int a = 0; a < N * N; a++) Mb[a] = M[a];
+					for (int a = 0; a < N; a++)
+						if (Mb[a * N + a] < jp.bie_threshold) Mb[a * N + a] = jp.bie_threshold;
+					spd_inverse(Mb, n, Mbi);
+					lambda_of(Jr, kr, n, Mbi, Mmod);
+				} else {
+					for (int a = 0; a < kr * kr; a++) Mmod[a] = ((a / kr) == (a % kr)) ? 1.0 : 0.0;
+				}
+				double pid[N], acc[N];
+				joint_control_law_rt<N>(jt, NR, i, q, dq, k, pid, acc);
+				double a1[N], a2[N], f[N], g[N];
+				mv_t(Ub, k, kr, acc, a1);
+				mv(Mp, kr, kr, a1, f);
+				mv_t(Ub, k, kr, pid, a2);
+				mv(Mmod, kr, kr, a2, g);
+				for (int c = 0; c < kr; c++) f[c] += g[c];
+				if (P.use_prev_torques) {  // - J_proj^T U M_partial U^T S Minv tau_prec
+					double mt[N], smt[N], ut[N], w[N];
+					mv(Minv, n, n, tau, mt);
+					mv(S, k, n, mt, smt);
+					mv_t(Ub, k, kr, smt, ut);
+					mv(Mp, kr, kr, ut, w);
+					for (int c = 0; c < kr; c++) f[c] -= w[c];
+				}
+				double uf[N], tj[N];
+				mv(Ub, k, kr, f, uf);
+				mv_t(Jp, k, n, uf, tj);
+				for (int j = 0; j < N; j++) tau[j] += tj[j];
+			}
 		}
+		// N_prec <- task.N * N_prec  (getTaskAndPreviousNullspace, RobotController.cpp:75)
+		double Nn[N * N];
+		mm(Nmat, n, n, Nprec, n, Nn);
+		for (int a = 0; a < N * N; a++) Nprec[a] = Nn[a];
 	}
 
 	if (P.torque_saturation)
@@ -544,14 +562,23 @@ static __device__ __noinline__ void singular_cycle_one(const OscProgram& P, cons
 	P.status[i] = status;
 }
 
-// One full control cycle for the robots in `sing_list` (count on the device, written by the fast kernel of the
-// same cycle).  Fixed grid, grid-stride over the list: with an empty list every thread exits at once.
-template <int N, int R, bool HAS_JT>
+// SVD-path kernel: the robots in `sing_list` (count on the device, written by the fast kernel of the same cycle).
+// Fixed grid, grid-stride over the list: with an empty list every thread exits at once.
+template <int N>
 __global__ void __launch_bounds__(64) osc_singular_kernel(const __grid_constant__ OscProgram P) {
 	const int32_t count = P.sing_count[P.sing_parity];
 	const int stride = gridDim.x * blockDim.x;
 	for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < count; slot += stride)
-		singular_cycle_one<N, R, HAS_JT>(P, (int64_t)P.sing_list[slot]);
+		generic_cycle_one<N>(P, (int64_t)P.sing_list[slot], OSC_STATUS_SINGULAR_PATH);
+}
+
+// Whole-batch kernel for hierarchies without a specialised fast kernel (partial joint tasks, several motion-force
+// tasks, ...): every robot takes the general path.
+template <int N>
+__global__ void __launch_bounds__(64) osc_generic_kernel(const __grid_constant__ OscProgram P) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P.n_robots) return;
+	generic_cycle_one<N>(P, i, 0u);
 }
 
 }  // namespace osc

@@ -417,5 +417,37 @@ DEVI void joint_control_law(const DevJt& t, int64_t NR, int64_t i, const double 
 	}
 }
 
+// Same law with a run-time task dimension (general hierarchies, osc_singular.cuh)
+template <int N>
+static __device__ __noinline__ void joint_control_law_rt(const DevJt& t, int64_t NR, int64_t i, const double (&q)[N], const double (&dq)[N], int k,
+														  double* pid, double* acc) {
+	double* st = t.st;
+	const osc_joint_params& p = t.p;
+	for (int a = 0; a < k; a++) {
+		double pos = 0.0, vel = 0.0;
+		for (int j = 0; j < N; j++) {
+			pos += t.S[a][j] * q[j];
+			vel += t.S[a][j] * dq[j];
+		}
+		const double e = pos - ST(JC_GOAL_POS, a);
+		const double vd = ST(JC_GOAL_VEL, a);
+		acc[a] = ST(JC_GOAL_ACC, a);
+		double I = ST(JC_INT, a);
+		I += e * t.dt;
+		ST(JC_INT, a) = I;
+		if (p.use_velocity_saturation) {
+			const double kvi = pinv_gain(p.kv[a]);
+			double vdes = -p.kp[a] * kvi * e - p.ki[a] * kvi * I;
+			if (vdes > p.saturation_velocity[a])
+				vdes = p.saturation_velocity[a];
+			else if (vdes < -p.saturation_velocity[a])
+				vdes = -p.saturation_velocity[a];
+			pid[a] = -p.kv[a] * (vel - vdes);
+		} else {
+			pid[a] = -p.kp[a] * e - p.kv[a] * (vel - vd) - p.ki[a] * I;
+		}
+	}
+}
+
 #undef ST
 }  // namespace osc

@@ -250,3 +250,60 @@ def test_singular_path_other_robots_and_partial_tasks():
             assert rel_err(tau, ref).max() < REL_TOL, (name, cycle)
         sing = np.array([len(t._singularity_handler._singularity_types) != 0 for t in omft])
         assert sing.sum() >= (N // 8 if name != "panda" else 1), name
+
+
+def test_general_hierarchies():
+    """Hierarchies without a specialised kernel run on the general-hierarchy kernel:
+    ex.06 (partial JointTask on slider + last joint, then a 6-DoF MotionForceTask) on the 8-DoF sliding-base Panda,
+    and [partial MotionForceTask (position), partial MotionForceTask (orientation), JointTask] on the Panda."""
+    import sai_primitives_b200 as sp
+    # ---- examples/06-partial_joint_task/06-partial_joint_task.cpp:108-128
+    name = "panda_sliding_base"
+    N = 48
+    q, dq, _ = sample_states(name, N)
+    link, pt = TASK_POINTS[name]
+    S = np.zeros((2, 8)); S[0, 0] = 1; S[1, 7] = 1
+    robot = sp.BatchedRobot(name, N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    pjt = sp.JointTask(robot, S, task_name="partial_joint_task")
+    mft = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt)))
+    ctrl = sp.RobotController(robot, [pjt, mft])
+    ob = OracleBatch(name, N); ob.set_state(q, dq)
+    opjt = ob.add_jt(S, name="partial_joint_task"); omft = ob.add_mft(link, (np.eye(3), np.array(pt))); ob.finalize()
+    _set_mft_goals(mft, omft, N)
+    gp = np.array([S @ q[i] + rng_for(i, stream=5).uniform(-0.2, 0.2, 2) for i in range(N)])
+    pjt.setGoalPosition(gp)
+    for i in range(N):
+        opjt[i].setGoalPosition(gp[i])
+    for cycle in range(3):
+        ctrl.updateControllerTaskModels()
+        tau = ctrl.computeControlTorques()
+        ref = ob.cycle()
+        assert (robot.status() & sp.capi.STATUS_UNHANDLED).sum() == 0
+        assert rel_err(tau, ref).max() < REL_TOL, cycle
+    # ---- two partial motion-force tasks + joint task
+    N = 48
+    q, dq, _ = sample_states("panda", N)
+    link, pt = TASK_POINTS["panda"]
+    xyz = [(1, 0, 0), (0, 1, 0), (0, 0, 1)]
+    robot = sp.BatchedRobot("panda", N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    t1 = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt)), xyz, [], task_name="position")
+    t2 = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt)), [], xyz, task_name="orientation")
+    jt = sp.JointTask(robot)
+    ctrl = sp.RobotController(robot, [t1, t2, jt])
+    ob = OracleBatch("panda", N); ob.set_state(q, dq)
+    o1 = ob.add_mft(link, (np.eye(3), np.array(pt)), xyz, [], name="position")
+    o2 = ob.add_mft(link, (np.eye(3), np.array(pt)), [], xyz, name="orientation")
+    oj = ob.add_jt(); ob.finalize()
+    _set_mft_goals(t1, o1, N); _set_mft_goals(t2, o2, N); _set_joint_goals(jt, oj, q, 7)
+    for cycle in range(3):
+        ctrl.updateControllerTaskModels()
+        tau = ctrl.computeControlTorques()
+        ref = ob.cycle()
+        assert rel_err(tau, ref).max() < REL_TOL, cycle
+    # a task after a full joint task is rejected like RobotController.cpp:45-51
+    robot = sp.BatchedRobot("panda", 4)
+    a = sp.JointTask(robot, task_name="a"); b = sp.JointTask(robot, task_name="b")
+    with pytest.raises(ValueError):
+        sp.RobotController(robot, [a, b])
