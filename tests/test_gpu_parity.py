@@ -307,3 +307,58 @@ def test_general_hierarchies():
     a = sp.JointTask(robot, task_name="a"); b = sp.JointTask(robot, task_name="b")
     with pytest.raises(ValueError):
         sp.RobotController(robot, [a, b])
+
+
+def test_config4_mixed_dof_batch():
+    """BASELINE config 4: one batch mixing Panda (7), PUMA-like (6) and planar RRRR (4) robots, grouped by model on
+    the host (sharding.ModelGroups), unfiltered states (singular robots included), two cycles."""
+    import sai_primitives_b200 as sp
+    from sai_primitives_b200.sharding import ModelGroups
+    specs = {"panda": (None, None), "puma_like": (None, None), "rrrr": ([(1, 0, 0), (0, 1, 0)], [(0, 0, 1)])}
+    N = 90
+    models = [("panda", "puma_like", "rrrr")[i % 3] for i in range(N)]
+
+    class GpuGroup:
+        def __init__(self, name, n):
+            self.name, self.n = name, n
+            self.robot = sp.BatchedRobot(name, n)
+            self.ctrl = None
+        def set_state(self, q, dq):
+            self.robot.setQ(q); self.robot.setDq(dq); self.robot.updateModel()
+            if self.ctrl is None:
+                link, pt = TASK_POINTS[self.name]
+                dt_, dr_ = specs[self.name]
+                self.mft = sp.MotionForceTask(self.robot, link, (np.eye(3), np.array(pt)), dt_, dr_)
+                self.jt = sp.JointTask(self.robot)
+                self.ctrl = sp.RobotController(self.robot, [self.mft, self.jt])
+        def cycle(self):
+            self.ctrl.updateControllerTaskModels()
+            return self.ctrl.computeControlTorques()
+
+    class OracleGroup:
+        def __init__(self, name, n):
+            self.name, self.n = name, n
+            self.ob = OracleBatch(name, n)
+            self.ready = False
+        def set_state(self, q, dq):
+            self.ob.set_state(q, dq)
+            if not self.ready:
+                link, pt = TASK_POINTS[self.name]
+                dt_, dr_ = specs[self.name]
+                self.ob.add_mft(link, (np.eye(3), np.array(pt)), dt_, dr_); self.ob.add_jt(); self.ob.finalize()
+                self.ready = True
+        def cycle(self):
+            return self.ob.cycle()
+
+    per_model = {nm: sample_states(nm, N)[:2] for nm in specs}
+    q = [per_model[m][0][i] for i, m in enumerate(models)]
+    dq = [per_model[m][1][i] for i, m in enumerate(models)]
+    gpu = ModelGroups(models, GpuGroup); ora = ModelGroups(models, OracleGroup)
+    gpu.set_state(q, dq); ora.set_state(q, dq)
+    for cycle in range(2):
+        a, b = gpu.cycle(), ora.cycle()
+        for i in range(N):
+            assert a[i].shape == b[i].shape
+            assert np.abs(a[i] - b[i]).max() <= REL_TOL * max(np.abs(b[i]).max(), 1e-9), (cycle, i, models[i])
+        q = [qi + 0.002 * dqi for qi, dqi in zip(q, dq)]
+        gpu.set_state(q, dq); ora.set_state(q, dq)
