@@ -15,10 +15,31 @@
 
 namespace osc {
 
+template <int N, int R, bool JT, bool FULL>
+static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
+	const unsigned grid = (unsigned)((P.n_robots + kCycleBlock - 1) / kCycleBlock);
+	constexpr int smem = 9 * N * kCycleBlock * (int)sizeof(double);  // body orientations staged between the two passes
+	static bool configured[64] = {false};  // per device: function attributes belong to the device's context
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64 || !configured[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(osc_cycle_kernel<N, R, JT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e != cudaSuccess) return e;
+		if (dev >= 0 && dev < 64) configured[dev] = true;
+	}
+	osc_cycle_kernel<N, R, JT, FULL><<<grid, kCycleBlock, smem, stream>>>(P);
+	return cudaGetLastError();
+}
+
 template <int N, int R, bool JT>
 static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
-	const unsigned grid = (unsigned)((P.n_robots + kCycleBlock - 1) / kCycleBlock);
-	osc_cycle_kernel<N, R, JT><<<grid, kCycleBlock, 0, stream>>>(P);
+	cudaError_t e0;
+	if constexpr (R == 6) {
+		e0 = (P.mft[0].full) ? launch_variant<N, R, JT, true>(P, stream) : launch_variant<N, R, JT, false>(P, stream);
+	} else {
+		e0 = launch_variant<N, R, JT, false>(P, stream);
+	}
+	if (e0 != cudaSuccess) return e0;
 	if constexpr (R > 0) {
 		// the SVD path for the robots the fast kernel handed over (usually none or few: exits immediately)
 		const long long want = (P.n_robots + 63) / 64;

@@ -218,4 +218,214 @@ DEVI void frame_pose(const KinDyn<N>& kd, int body, const double Rf[9], const do
 	mat3_mul(Rb, Rf, R);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Variant used by the fused cycle kernel: the body orientations produced by the forward pass are staged in
+// shared memory (element e of this thread at smt[e * sms]) instead of 9 N registers, joints whose axis is the
+// local z axis and bodies with isotropic inertia take short cuts (warp-uniform branches on model constants),
+// and only the lower triangle of M is written.
+template <int N>
+struct KinDynS {
+	double a[N][3];	 // joint axis, world
+	double p[N][3];	 // joint origin, world
+	double M[N][N];	 // lower triangle valid
+	double g[N];
+};
+
+template <int N>
+DEVI void forward_kinematics_s(const DevModel& m, const double (&q)[N], KinDynS<N>& kd, double* smt, int sms) {
+	double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+	double p[3] = {0, 0, 0};
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		double t[3];
+		mat3_vec(R, m.t_fix[i], t);
+		p[0] += t[0];
+		p[1] += t[1];
+		p[2] += t[2];
+		double Rn[9];
+		mat3_mul(R, m.R_fix[i], Rn);
+		const bool axis_z = (m.axis[i][0] == 0.0) && (m.axis[i][1] == 0.0) && (m.axis[i][2] == 1.0);
+		if (m.jtype[i] == 0) {
+			double s, c;
+			sincos(q[i], &s, &c);
+			if (axis_z) {  // R = Rn Rz(q): only the first two columns mix
+#pragma unroll
+				for (int r = 0; r < 3; r++) {
+					const double c0 = Rn[3 * r], c1 = Rn[3 * r + 1];
+					R[3 * r] = c * c0 + s * c1;
+					R[3 * r + 1] = c * c1 - s * c0;
+					R[3 * r + 2] = Rn[3 * r + 2];
+				}
+				kd.a[i][0] = R[2];
+				kd.a[i][1] = R[5];
+				kd.a[i][2] = R[8];
+			} else {
+				double Rq[9];
+				axis_angle(m.axis[i], s, c, Rq);
+				mat3_mul(Rn, Rq, R);
+				mat3_vec(R, m.axis[i], kd.a[i]);
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < 9; k++) R[k] = Rn[k];
+			mat3_vec(R, m.axis[i], kd.a[i]);
+			p[0] += kd.a[i][0] * q[i];
+			p[1] += kd.a[i][1] * q[i];
+			p[2] += kd.a[i][2] * q[i];
+		}
+#pragma unroll
+		for (int k = 0; k < 9; k++) smt[(9 * i + k) * sms] = R[k];
+		kd.p[i][0] = p[0];
+		kd.p[i][1] = p[1];
+		kd.p[i][2] = p[2];
+	}
+}
+
+template <int N, bool WITH_GRAVITY>
+DEVI void mass_matrix_s(const DevModel& m, KinDynS<N>& kd, const double* smt, int sms) {
+	double cm = 0.0, ch[3] = {0, 0, 0};
+	double cI[6] = {0, 0, 0, 0, 0, 0};	// xx xy xz yy yz zz
+#pragma unroll
+	for (int i = N - 1; i >= 0; i--) {
+		double R[9];
+#pragma unroll
+		for (int k = 0; k < 9; k++) R[k] = smt[(9 * i + k) * sms];
+		const double* Ib = m.inertia[i];
+		const bool iso = (Ib[1] == 0.0) && (Ib[2] == 0.0) && (Ib[4] == 0.0) && (Ib[0] == Ib[3]) && (Ib[0] == Ib[5]);
+		double Iw[6];
+		if (iso) {	// R (k I) R^T = k I
+			Iw[0] = Ib[0];
+			Iw[1] = 0.0;
+			Iw[2] = 0.0;
+			Iw[3] = Ib[0];
+			Iw[4] = 0.0;
+			Iw[5] = Ib[0];
+		} else {
+			double T[9];  // T = R * I
+#pragma unroll
+			for (int r = 0; r < 3; r++) {
+				T[3 * r + 0] = R[3 * r] * Ib[0] + R[3 * r + 1] * Ib[1] + R[3 * r + 2] * Ib[2];
+				T[3 * r + 1] = R[3 * r] * Ib[1] + R[3 * r + 1] * Ib[3] + R[3 * r + 2] * Ib[4];
+				T[3 * r + 2] = R[3 * r] * Ib[2] + R[3 * r + 1] * Ib[4] + R[3 * r + 2] * Ib[5];
+			}
+			Iw[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2];
+			Iw[1] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5];
+			Iw[2] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8];
+			Iw[3] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5];
+			Iw[4] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8];
+			Iw[5] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8];
+		}
+		double c[3];
+		mat3_vec(R, m.com[i], c);
+		c[0] += kd.p[i][0];
+		c[1] += kd.p[i][1];
+		c[2] += kd.p[i][2];
+		const double mi = m.mass[i];
+		const double cc = dot3(c, c);
+		cm += mi;
+		ch[0] += mi * c[0];
+		ch[1] += mi * c[1];
+		ch[2] += mi * c[2];
+		cI[0] += Iw[0] + mi * (cc - c[0] * c[0]);
+		cI[1] += Iw[1] - mi * c[0] * c[1];
+		cI[2] += Iw[2] - mi * c[0] * c[2];
+		cI[3] += Iw[3] + mi * (cc - c[1] * c[1]);
+		cI[4] += Iw[4] - mi * c[1] * c[2];
+		cI[5] += Iw[5] + mi * (cc - c[2] * c[2]);
+
+		double w[3], vo[3];
+		if (m.jtype[i] == 0) {
+			w[0] = kd.a[i][0];
+			w[1] = kd.a[i][1];
+			w[2] = kd.a[i][2];
+			cross3(kd.p[i], kd.a[i], vo);
+		} else {
+			w[0] = w[1] = w[2] = 0.0;
+			vo[0] = kd.a[i][0];
+			vo[1] = kd.a[i][1];
+			vo[2] = kd.a[i][2];
+		}
+		double f[3], no[3], t1[3];
+		cross3(w, ch, t1);
+		f[0] = cm * vo[0] + t1[0];
+		f[1] = cm * vo[1] + t1[1];
+		f[2] = cm * vo[2] + t1[2];
+		cross3(ch, vo, t1);
+		no[0] = cI[0] * w[0] + cI[1] * w[1] + cI[2] * w[2] + t1[0];
+		no[1] = cI[1] * w[0] + cI[3] * w[1] + cI[4] * w[2] + t1[1];
+		no[2] = cI[2] * w[0] + cI[4] * w[1] + cI[5] * w[2] + t1[2];
+#pragma unroll
+		for (int j = 0; j <= i; j++) {
+			// s_j . F_i = a_j . (n_o + f x p_j) for a revolute joint j,  a_j . f for a prismatic one
+			if (m.jtype[j] == 0) {
+				double fxp[3];
+				cross3(f, kd.p[j], fxp);
+				kd.M[i][j] = kd.a[j][0] * (no[0] + fxp[0]) + kd.a[j][1] * (no[1] + fxp[1]) + kd.a[j][2] * (no[2] + fxp[2]);
+			} else {
+				kd.M[i][j] = dot3(kd.a[j], f);
+			}
+		}
+		if (WITH_GRAVITY) {
+			double hg[3];
+			cross3(ch, m.gravity, hg);
+			kd.g[i] = -(dot3(w, hg) + cm * dot3(vo, m.gravity));
+		}
+	}
+}
+
+// pose of a frame (Rf, tf given in the body frame) in the world; body orientation read back from shared memory
+template <int N>
+DEVI void frame_pose_s(const KinDynS<N>& kd, int body, const double Rf[9], const double tf[3], double x[3], double R[9],
+						const double* smt, int sms) {
+	double Rb[9], pb[3];
+	if (body >= 0) {
+#pragma unroll
+		for (int k = 0; k < 9; k++) Rb[k] = smt[(9 * body + k) * sms];
+	} else {
+#pragma unroll
+		for (int k = 0; k < 9; k++) Rb[k] = (k % 4 == 0) ? 1.0 : 0.0;
+	}
+	pb[0] = pb[1] = pb[2] = 0.0;
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		if (i == body) {
+			pb[0] = kd.p[i][0];
+			pb[1] = kd.p[i][1];
+			pb[2] = kd.p[i][2];
+		}
+	}
+	double t[3];
+	mat3_vec(Rb, tf, t);
+	x[0] = pb[0] + t[0];
+	x[1] = pb[1] + t[1];
+	x[2] = pb[2] + t[2];
+	mat3_mul(Rb, Rf, R);
+}
+
+// column j of the 6 x n world-frame Jacobian (linear rows first) of point x fixed to body `body`
+template <int N>
+DEVI void jacobian_column(const DevModel& m, const KinDynS<N>& kd, int body, const double x[3], int j, double c6[6]) {
+	if (j <= body) {
+		if (m.jtype[j] == 0) {
+			double d[3] = {x[0] - kd.p[j][0], x[1] - kd.p[j][1], x[2] - kd.p[j][2]};
+			double v[3];
+			cross3(kd.a[j], d, v);
+			c6[0] = v[0];
+			c6[1] = v[1];
+			c6[2] = v[2];
+			c6[3] = kd.a[j][0];
+			c6[4] = kd.a[j][1];
+			c6[5] = kd.a[j][2];
+		} else {
+			c6[0] = kd.a[j][0];
+			c6[1] = kd.a[j][1];
+			c6[2] = kd.a[j][2];
+			c6[3] = c6[4] = c6[5] = 0.0;
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < 6; k++) c6[k] = 0.0;
+	}
+}
+
 }  // namespace osc

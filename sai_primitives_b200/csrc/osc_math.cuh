@@ -45,9 +45,10 @@ DEVI void mat3_mul_bt(const double A[9], const double B[9], double C[9]) {
 }
 
 // In-place Cholesky of the lower triangle of a symmetric positive definite matrix: A = L L^T.
-// Returns false when a pivot is not positive (matrix not positive definite).
+// invd[j] = 1 / L[j][j] is kept so that the triangular solves multiply instead of divide (one FP64 reciprocal
+// per pivot instead of one division per solve step).  Returns false when a pivot is not positive.
 template <int N>
-DEVI bool cholesky_lower(double (&A)[N][N]) {
+DEVI bool cholesky_lower(double (&A)[N][N], double (&invd)[N]) {
 	bool ok = true;
 #pragma unroll
 	for (int j = 0; j < N; j++) {
@@ -55,9 +56,9 @@ DEVI bool cholesky_lower(double (&A)[N][N]) {
 #pragma unroll
 		for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
 		ok = ok && (d > 0.0);
-		const double l = sqrt(d);
-		const double inv = 1.0 / l;
-		A[j][j] = l;
+		const double inv = rsqrt(d);
+		invd[j] = inv;
+		A[j][j] = d * inv;
 #pragma unroll
 		for (int i = j + 1; i < N; i++) {
 			double s = A[i][j];
@@ -71,24 +72,24 @@ DEVI bool cholesky_lower(double (&A)[N][N]) {
 
 // x <- L^-1 x   (L lower triangular, N x N)
 template <int N>
-DEVI void solve_lower(const double (&L)[N][N], double (&x)[N]) {
+DEVI void solve_lower(const double (&L)[N][N], const double (&invd)[N], double (&x)[N]) {
 #pragma unroll
 	for (int i = 0; i < N; i++) {
 		double s = x[i];
 #pragma unroll
 		for (int k = 0; k < i; k++) s -= L[i][k] * x[k];
-		x[i] = s / L[i][i];
+		x[i] = s * invd[i];
 	}
 }
 // x <- L^-T x
 template <int N>
-DEVI void solve_lower_t(const double (&L)[N][N], double (&x)[N]) {
+DEVI void solve_lower_t(const double (&L)[N][N], const double (&invd)[N], double (&x)[N]) {
 #pragma unroll
 	for (int i = N - 1; i >= 0; i--) {
 		double s = x[i];
 #pragma unroll
 		for (int k = i + 1; k < N; k++) s -= L[k][i] * x[k];
-		x[i] = s / L[i][i];
+		x[i] = s * invd[i];
 	}
 }
 // y = L x
@@ -104,36 +105,35 @@ DEVI void mul_lower(const double (&L)[N][N], const double (&x)[N], double (&y)[N
 }
 // x <- (L L^T)^-1 x
 template <int N>
-DEVI void solve_spd(const double (&L)[N][N], double (&x)[N]) {
-	solve_lower<N>(L, x);
-	solve_lower_t<N>(L, x);
+DEVI void solve_spd(const double (&L)[N][N], const double (&invd)[N], double (&x)[N]) {
+	solve_lower<N>(L, invd, x);
+	solve_lower_t<N>(L, invd, x);
 }
 
-// x <- R^-T x  then  x <- R^-1 x  with R upper triangular R x R stored in X[C+i][j], i <= j
-// i.e. x <- (R^T R)^-1 x
+// x <- (R^T R)^-1 x  with R upper triangular R x R stored in X[C+i][j], i <= j, rinv[i] = 1 / R[i][i]
 template <int N, int R, int C>
-DEVI void solve_rtr(const double (&X)[N][R], double (&x)[R]) {
+DEVI void solve_rtr(const double (&X)[N][R], const double (&rinv)[R], double (&x)[R]) {
 #pragma unroll
 	for (int i = 0; i < R; i++) {  // R^T z = x (forward)
 		double s = x[i];
 #pragma unroll
 		for (int k = 0; k < i; k++) s -= X[C + k][i] * x[k];
-		x[i] = s / X[C + i][i];
+		x[i] = s * rinv[i];
 	}
 #pragma unroll
 	for (int i = R - 1; i >= 0; i--) {	// R y = z (backward)
 		double s = x[i];
 #pragma unroll
 		for (int k = i + 1; k < R; k++) s -= X[C + i][k] * x[k];
-		x[i] = s / X[C + i][i];
+		x[i] = s * rinv[i];
 	}
 }
 
 // Householder QR of rows C..N-1 of X (N x R), in place:
 //   on exit X[C+i][j] (i <= j) holds R; reflector j is v_j with v_j[C+j] = vhead[j] and
-//   v_j[C+j+1..N-1] stored in X below the diagonal; H_j = I - beta[j] v_j v_j^T.
+//   v_j[C+j+1..N-1] stored in X below the diagonal; H_j = I - beta[j] v_j v_j^T;  rinv[j] = 1 / R[j][j].
 template <int N, int R, int C>
-DEVI void householder_qr(double (&X)[N][R], double (&vhead)[R], double (&beta)[R]) {
+DEVI void householder_qr(double (&X)[N][R], double (&vhead)[R], double (&beta)[R], double (&rinv)[R]) {
 #pragma unroll
 	for (int j = 0; j < R; j++) {
 		constexpr int dummy = 0;
@@ -142,9 +142,11 @@ DEVI void householder_qr(double (&X)[N][R], double (&vhead)[R], double (&beta)[R
 		double nrm2 = 0.0;
 #pragma unroll
 		for (int i = k; i < N; i++) nrm2 += X[i][j] * X[i][j];
-		const double nrm = sqrt(nrm2);
+		const double inrm = rsqrt(nrm2);
+		const double nrm = nrm2 * inrm;
 		const double x0 = X[k][j];
 		const double alpha = (x0 >= 0.0) ? -nrm : nrm;
+		rinv[j] = (x0 >= 0.0) ? -inrm : inrm;
 		const double v0 = x0 - alpha;
 		// v^T v = nrm2 - 2 alpha x0 + alpha^2 = 2 (nrm2 - alpha x0)
 		const double vv = 2.0 * (nrm2 - alpha * x0);
@@ -244,7 +246,8 @@ DEVI bool sound_nonsingular(const double (&JT)[N][R], double thr, double abs_tol
 	const double shift = thr * thr * hi;
 #pragma unroll
 	for (int a = 0; a < R; a++) G[a][a] -= shift;
-	return cholesky_lower<R>(G);
+	double invd[R];
+	return cholesky_lower<R>(G, invd);
 }
 
 }  // namespace osc

@@ -406,7 +406,13 @@ static __device__ __noinline__ void generic_cycle_one(const OscProgram& P, const
 
 			// ---- MotionForceTask::computeTorques (:278-509) + SingularityHandler::computeTorques (:297-368)
 			double fstar[6], F[6];
-			mft_control_law<N>(t, NR, i, x, Rc, JT0, dq, P.write_observers != 0, fstar, F, status);
+			double vv[3] = {0, 0, 0}, ww[3] = {0, 0, 0};
+			for (int j = 0; j < N; j++)
+				for (int k = 0; k < 3; k++) {
+					vv[k] += JT0[j][k] * dq[j];
+					ww[k] += JT0[j][3 + k] * dq[j];
+				}
+			mft_control_law(t, NR, i, x, Rc, vv, ww, P.write_observers != 0, fstar, F, status);
 			double tt[N];
 			for (int j = 0; j < N; j++) tt[j] = 0.0;
 			double a[6], b[6], c[6];

@@ -158,25 +158,15 @@ DEVI void scale_to_norm(double v[3], double maxn) {
 // pseudo-inverse of a diagonal gain entry (SaiModel::computePseudoInverse of a diagonal matrix)
 DEVI double pinv_gain(double k) { return (k > 1e-6) ? 1.0 / k : 0.0; }
 
-// x, R: pose of the compliant frame in the world; JT0: full 6 x n Jacobian (transposed storage).
-// Outputs the unit-mass force f* and the force-related terms F (world axes, 6 each).
-template <int N>
-DEVI void mft_control_law(const DevMft& t, int64_t NR, int64_t i, const double x[3], const double R[9],
-						  const double (&JT0)[N][6], const double (&dq)[N], bool write_observers, double fstar[6],
-						  double F[6], uint32_t& status) {
+// x, R: pose of the compliant frame in the world; v_in, w_in: J0 dq of the full (unprojected) Jacobian.
+// Outputs the unit-mass force f* and the force-related terms F (world axes, 6 each); returns false when F is
+// identically zero (pure motion control of a full task), so that callers can skip it.
+DEVI bool mft_control_law(const DevMft& t, int64_t NR, int64_t i, const double x[3], const double R[9], const double v_in[3],
+						  const double w_in[3], bool write_observers, double fstar[6], double F[6], uint32_t& status) {
 	double* st = t.st;
 	const osc_mft_params& p = t.p;
 	const double dt = t.dt;
-	double v[3] = {0, 0, 0}, w[3] = {0, 0, 0};
-#pragma unroll
-	for (int j = 0; j < N; j++) {
-		v[0] += JT0[j][0] * dq[j];
-		v[1] += JT0[j][1] * dq[j];
-		v[2] += JT0[j][2] * dq[j];
-		w[0] += JT0[j][3] * dq[j];
-		w[1] += JT0[j][4] * dq[j];
-		w[2] += JT0[j][5] * dq[j];
-	}
+	double v[3] = {v_in[0], v_in[1], v_in[2]}, w[3] = {w_in[0], w_in[1], w_in[2]};
 	if (!t.full) {	// _jacobian = P * J0  (MotionForceTask.cpp:280-282, 293-298)
 		double tv[3], tw[3];
 		mat3_vec(t.Pt, v, tv);
@@ -198,6 +188,56 @@ DEVI void mft_control_law(const DevMft& t, int64_t NR, int64_t i, const double x
 
 	double ori_err_goal[3];
 	orientation_error(Rd, R, ori_err_goal);	 // :291-292 (desired == goal with OTG off)
+
+	// Pure motion control of a full task (no force/moment space, open loop): every sigma is 0 or the identity
+	// (MotionForceTask.cpp:892-971), the force-related terms vanish and only the two PID laws remain.
+	if (t.full && p.force_space_dimension == 0 && p.moment_space_dimension == 0 && !p.closed_loop_force_control &&
+		!p.closed_loop_moment_control) {
+		double Ip[3], Io[3];
+		load3(st, NR, i, MC_INT_POS, Ip);
+		load3(st, NR, i, MC_INT_ORI, Io);
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			const double ex = x[k] - xd[k];
+			Ip[k] += ex * dt;
+			Io[k] += ori_err_goal[k] * dt;
+			if (!p.use_velocity_saturation) {
+				fstar[k] = ad[k] - p.kp_pos[k] * ex - p.kv_pos[k] * (v[k] - vd[k]) - p.ki_pos[k] * Ip[k];
+				fstar[3 + k] = ald[k] - p.kp_ori[k] * ori_err_goal[k] - p.kv_ori[k] * (w[k] - wd[k]) - p.ki_ori[k] * Io[k];
+			}
+			F[k] = 0.0;
+			F[3 + k] = 0.0;
+		}
+		if (p.use_velocity_saturation) {
+			double vdes[3], wdes[3];
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				const double kvi = pinv_gain(p.kv_pos[k]), kwi = pinv_gain(p.kv_ori[k]);
+				vdes[k] = -p.kp_pos[k] * kvi * (x[k] - xd[k]) - p.ki_pos[k] * kvi * Ip[k];
+				wdes[k] = -p.kp_ori[k] * kwi * ori_err_goal[k] - p.ki_ori[k] * kwi * Io[k];
+			}
+			scale_to_norm(vdes, p.linear_saturation_velocity);
+			scale_to_norm(wdes, p.angular_saturation_velocity);
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				fstar[k] = ad[k] - p.kv_pos[k] * (v[k] - vdes[k]);
+				fstar[3 + k] = ald[k] - p.kv_ori[k] * (w[k] - wdes[k]);
+			}
+		}
+		store3(st, NR, i, MC_INT_POS, Ip);
+		store3(st, NR, i, MC_INT_ORI, Io);
+		store3(st, NR, i, MC_CUR_POS, x);
+#pragma unroll
+		for (int k = 0; k < 9; k++) ST(MC_CUR_ORI, k) = R[k];
+		if (write_observers) {
+			store3(st, NR, i, MC_CUR_LINVEL, v);
+			store3(st, NR, i, MC_CUR_ANGVEL, w);
+			store3(st, NR, i, MC_ORI_ERROR, ori_err_goal);
+#pragma unroll
+			for (int k = 0; k < 6; k++) ST(MC_UNIT_MASS_FORCE, k) = fstar[k];
+		}
+		return false;
+	}
 
 	// selection matrices
 	const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -373,6 +413,7 @@ DEVI void mft_control_law(const DevMft& t, int64_t NR, int64_t i, const double x
 		for (int k = 0; k < 6; k++) ST(MC_UNIT_MASS_FORCE, k) = fstar[k];
 	}
 	(void)I3;
+	return true;
 }
 
 // JointTask PID in task coordinates: returns t (pid "torques") and the desired acceleration.
