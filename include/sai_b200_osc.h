@@ -263,6 +263,9 @@ int osc_update_task_models(osc_handle* h);
 int osc_compute_control_torques(osc_handle* h, double* tau_out, int mem_kind);
 /* fused cycle: set_state + update_task_models + compute_control_torques in one launch */
 int osc_step(osc_handle* h, const double* q, const double* dq, double* tau_out, int mem_kind);
+/* osc_step without the final synchronisation: with OSC_MEM_HOST the buffers must be page-locked and stay valid (and
+ * tau_out unread) until osc_sync(h) returns; lets a caller pipeline the host<->device copies of several handles */
+int osc_step_async(osc_handle* h, const double* q, const double* dq, double* tau_out, int mem_kind);
 int osc_get_status(osc_handle* h, uint32_t* flags_out, int mem_kind);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t osc_launch_count(const osc_handle* h);

@@ -172,6 +172,7 @@ SYMBOLS = {
     "osc_update_task_models": (C.c_int, [_H]),
     "osc_compute_control_torques": (C.c_int, [_H, _PD, C.c_int]),
     "osc_step": (C.c_int, [_H, _PD, _PD, _PD, C.c_int]),
+    "osc_step_async": (C.c_int, [_H, _PD, _PD, _PD, C.c_int]),
     "osc_get_status": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "osc_launch_count": (C.c_int64, [_H]),
     "osc_eval_model": (C.c_int, [_H, C.c_int, C.POINTER(LinkFrame), C.POINTER(D), _PD, _PD, _PD, _PD, _PD, C.c_int]),

@@ -971,7 +971,7 @@ int osc_update_task_models(osc_handle* h) {
 	return OSC_OK;
 }
 
-static int run_cycle(osc_handle* h, double* tau_out, int mem_kind) {
+static int run_cycle(osc_handle* h, double* tau_out, int mem_kind, bool sync_host = true) {
 	if (!h->finalized) return fail(h, OSC_ERR_STATE, "controller not finalized");
 	if (!tau_out) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null torque output");
 	if (mem_kind != OSC_MEM_HOST && mem_kind != OSC_MEM_DEVICE) return fail(h, OSC_ERR_INVALID_ARGUMENT, "bad mem_kind");
@@ -985,7 +985,7 @@ static int run_cycle(osc_handle* h, double* tau_out, int mem_kind) {
 	h->prog.sing_parity ^= 1;
 	if (mem_kind == OSC_MEM_HOST) {
 		CUDA_TRY(h, cudaMemcpyAsync(tau_out, h->d_tau, (size_t)h->model.n * h->NR * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-		CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+		if (sync_host) CUDA_TRY(h, cudaStreamSynchronize(h->stream));
 	}
 	return OSC_OK;
 }
@@ -995,8 +995,19 @@ int osc_compute_control_torques(osc_handle* h, double* tau_out, int mem_kind) {
 	return run_cycle(h, tau_out, mem_kind);
 }
 
+static int step_impl(osc_handle* h, const double* q, const double* dq, double* tau_out, int mem_kind, bool sync_host);
+
 int osc_step(osc_handle* h, const double* q, const double* dq, double* tau_out, int mem_kind) {
 	ENTER(h);
+	return step_impl(h, q, dq, tau_out, mem_kind, true);
+}
+
+int osc_step_async(osc_handle* h, const double* q, const double* dq, double* tau_out, int mem_kind) {
+	ENTER(h);
+	return step_impl(h, q, dq, tau_out, mem_kind, false);
+}
+
+static int step_impl(osc_handle* h, const double* q, const double* dq, double* tau_out, int mem_kind, bool sync_host) {
 	if (!h->finalized) return fail(h, OSC_ERR_STATE, "controller not finalized");
 	if (!q || !dq) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null state pointer");
 	const size_t bytes = (size_t)h->model.n * h->NR * sizeof(double);
@@ -1012,7 +1023,7 @@ int osc_step(osc_handle* h, const double* q, const double* dq, double* tau_out, 
 		return fail(h, OSC_ERR_INVALID_ARGUMENT, "bad mem_kind");
 	}
 	h->models_armed = true;
-	return run_cycle(h, tau_out, mem_kind);
+	return run_cycle(h, tau_out, mem_kind, sync_host);
 }
 
 int osc_get_status(osc_handle* h, uint32_t* flags_out, int mem_kind) {

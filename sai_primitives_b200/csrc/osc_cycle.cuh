@@ -37,15 +37,18 @@ namespace osc {
 #define OSC_MIN_BLOCKS 1
 #endif
 
-// h_i = sqrt(max(thr - M_ii, 0)):  M_BIE = M + diag(h_i^2).  Returns the number of clamped entries.
+// M_BIE = M + diag(d),  d_i = max(thr - M_ii, 0).  Returns the number of clamped entries k; for k == 1 the update is
+// the rank-one matrix  delta e e^T  (e = indicator of the clamped entry, delta = sum(d)), which needs no square root.
 template <int N>
-DEVI int bie_shift(const double (&Mdiag)[N], double thr, double (&h)[N]) {
+DEVI int bie_shift(const double (&Mdiag)[N], double thr, double (&d)[N], double& delta) {
 	int k = 0;
+	delta = 0.0;
 #pragma unroll
 	for (int j = 0; j < N; j++) {
-		const double d = thr - Mdiag[j];
-		h[j] = (d > 0.0) ? sqrt(d) : 0.0;
-		k += (d > 0.0) ? 1 : 0;
+		const double dj = thr - Mdiag[j];
+		d[j] = (dj > 0.0) ? dj : 0.0;
+		delta += d[j];
+		k += (dj > 0.0) ? 1 : 0;
 	}
 	return k;
 }
@@ -53,7 +56,7 @@ DEVI int bie_shift(const double (&Mdiag)[N], double thr, double (&h)[N]) {
 // Cholesky of M_BIE re-assembled from M = L L^T (the lower triangle of M is overwritten by its factor):
 // general route for two or more clamped entries.
 template <int N>
-DEVI void bie_cholesky_from_factor(const double (&L)[N][N], const double (&h)[N], double (&Lb)[N][N], double (&invdb)[N]) {
+DEVI void bie_cholesky_from_factor(const double (&L)[N][N], const double (&d)[N], double (&Lb)[N][N], double (&invdb)[N]) {
 #pragma unroll
 	for (int r = 0; r < N; r++)
 #pragma unroll
@@ -61,9 +64,26 @@ DEVI void bie_cholesky_from_factor(const double (&L)[N][N], const double (&h)[N]
 			double s = 0.0;
 #pragma unroll
 			for (int k = 0; k <= c; k++) s += L[r][k] * L[c][k];
-			Lb[r][c] = (r == c) ? s + h[r] * h[r] : s;
+			Lb[r][c] = (r == c) ? s + d[r] : s;
 		}
 	cholesky_lower<N>(Lb, invdb);
+}
+
+// y = B^T v: the six world-frame components of a task vector reduced to the R coordinates of the task range
+// (identity for a full task)
+template <int R, bool FULL>
+DEVI void reduce_task_vector(const DevMft& t, const double (&v6)[6], double (&y)[R]) {
+#pragma unroll
+	for (int a = 0; a < R; a++) {
+		if constexpr (FULL) {
+			y[a] = v6[a < 6 ? a : 0];
+		} else {
+			double s = 0.0;
+#pragma unroll
+			for (int k = 0; k < 6; k++) s += t.B[k][a] * v6[k];
+			y[a] = s;
+		}
+	}
 }
 
 // Signature <N, R, HAS_JT, FULL>:  R = rank of a leading MotionForceTask (0: none), FULL = that task controls all six
@@ -79,7 +99,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	if (i >= NR) return;
 	const DevModel& mdl = P.model;
 	double* smt = sm + threadIdx.x;
-	const int sms = blockDim.x;
+	constexpr int sms = kCycleBlock;  // the launcher always uses kCycleBlock threads per block
 
 	double q[N], dq[N];
 #pragma unroll
@@ -89,10 +109,6 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	}
 	KinDynS<N> kd;
 	forward_kinematics_s<N>(mdl, q, kd, smt, sms);
-	if (P.gravity_comp)
-		mass_matrix_s<N, true>(mdl, kd, smt, sms);
-	else
-		mass_matrix_s<N, false>(mdl, kd, smt, sms);
 
 	double tau[N];
 #pragma unroll
@@ -101,6 +117,10 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 
 	if constexpr (R == 0) {
 		// ---- a full JointTask alone: N_prec = I, range = I:  tau = M qdd_d + M_mod t   (JointTask.cpp:348-355)
+		if (P.gravity_comp)
+			mass_matrix_s<N, true>(mdl, kd, smt, sms);
+		else
+			mass_matrix_s<N, false>(mdl, kd, smt, sms);
 		const DevJt& t = P.jt[0];
 		const osc_joint_params& p = t.p;
 		double pid[N], acc[N];
@@ -127,36 +147,38 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		const osc_mft_params& p = t.p;
 		double x[3], Rc[9];
 		frame_pose_s<N>(kd, t.body, t.ctrl_R, t.ctrl_t, x, Rc, smt, sms);
-		// task rows J_t = B^T J0, stored transposed (N x R); for a full task J_t = J0
-		double JtT[N][R];
-		double v[3] = {0, 0, 0}, w[3] = {0, 0, 0};	// J0 dq
-#pragma unroll
-		for (int j = 0; j < N; j++) {
-			double c6[6];
-			jacobian_column<N>(mdl, kd, t.body, x, j, c6);
-#pragma unroll
-			for (int k = 0; k < 3; k++) {
-				v[k] += c6[k] * dq[j];
-				w[k] += c6[3 + k] * dq[j];
-			}
-			if constexpr (FULL) {
-#pragma unroll
-				for (int a = 0; a < R; a++) JtT[j][a] = c6[a < 6 ? a : 0];
-			} else {
-#pragma unroll
-				for (int a = 0; a < R; a++) {
-					double s = 0.0;
-#pragma unroll
-					for (int k = 0; k < 6; k++) s += c6[k] * t.B[k][a];
-					JtT[j][a] = s;
-				}
-			}
-		}
-		// Branch decision of SingularityHandler::updateTaskModel (:83-105), taken before any task state is touched:
-		// robots that are not provably non-singular are appended (warp-aggregated) to the list of the general-path
-		// kernel and leave this kernel.
-		const bool flagged = !sound_nonsingular<N, R>(JtT, p.s_max, p.s_abs_tol);
+
+		// ---- pass 1 over the Jacobian columns (never stored): G = J_t J_t^T and the task velocity J0 dq
+		double v[3] = {0, 0, 0}, w[3] = {0, 0, 0};
 		{
+			double G[R][R];
+#pragma unroll
+			for (int a = 0; a < R; a++)
+#pragma unroll
+				for (int b = 0; b < R; b++) G[a][b] = 0.0;
+#pragma unroll
+			for (int j = 0; j < N; j++) {
+				double c6[6], cr[R];
+				jacobian_column<N>(mdl, kd, t.body, x, j, c6);
+#pragma unroll
+				for (int k = 0; k < 3; k++) {
+					v[k] += c6[k] * dq[j];
+					w[k] += c6[3 + k] * dq[j];
+				}
+				reduce_task_vector<R, FULL>(t, c6, cr);
+#pragma unroll
+				for (int a = 0; a < R; a++)
+#pragma unroll
+					for (int b = 0; b <= a; b++) G[a][b] += cr[a] * cr[b];
+			}
+#pragma unroll
+			for (int a = 0; a < R; a++)
+#pragma unroll
+				for (int b = a + 1; b < R; b++) G[a][b] = G[b][a];
+			// Branch decision of SingularityHandler::updateTaskModel (:83-105), taken before any task state is touched and
+			// before the dynamics are evaluated: robots that are not provably non-singular are appended
+			// (warp-aggregated) to the list of the general-path kernel and leave this kernel.
+			const bool flagged = !sound_nonsingular_gram<R>(G, p.s_max, p.s_abs_tol);
 			const unsigned act = __activemask();
 			const unsigned m = __ballot_sync(act, flagged);
 			if (flagged) {
@@ -179,56 +201,61 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			t.ist[(int64_t)MI_HIST_SIZE * NR + i] = 0;
 		}
 
-		// M = L L^T in place; the diagonal of M is all the bounded-inertia variant needs later
-		double Mdiag[N], invd[N];
+		// ---- dynamics: M (composite rigid bodies), M = L L^T in place, factor staged in shared memory (the body
+		// orientations are dead from here on); only diag(M) is kept for the bounded-inertia variant
+		if (P.gravity_comp)
+			mass_matrix_s<N, true>(mdl, kd, smt, sms);
+		else
+			mass_matrix_s<N, false>(mdl, kd, smt, sms);
+		double Mdiag[N];
+		SmTri<N, kCycleBlock> Ls{smt};
+		{
+			double invd[N];
 #pragma unroll
-		for (int j = 0; j < N; j++) Mdiag[j] = kd.M[j][j];
-		cholesky_lower<N>(kd.M, invd);
-		double(&L)[N][N] = kd.M;
-
-		double fstar[6], F[6];
-		const bool has_F = mft_control_law(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status);
-		double yf[R], yF[R];
-#pragma unroll
-		for (int a = 0; a < R; a++) {
-			if constexpr (FULL) {
-				yf[a] = fstar[a < 6 ? a : 0];
-				yF[a] = F[a < 6 ? a : 0];
-			} else {
-				double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-				for (int k = 0; k < 6; k++) {
-					s1 += t.B[k][a] * fstar[k];
-					s2 += t.B[k][a] * F[k];
-				}
-				yf[a] = s1;
-				yF[a] = s2;
-			}
+			for (int j = 0; j < N; j++) Mdiag[j] = kd.M[j][j];
+			cholesky_lower<N>(kd.M, invd);
+			Ls.store(kd.M, invd);
 		}
 
-		// X = L^-1 J_t^T, all R columns row by row
+		double yf[R], yF[R];
+		bool has_F;
+		{
+			double fstar[6], F[6];
+			has_F = mft_control_law(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status);
+			reduce_task_vector<R, FULL>(t, fstar, yf);
+			reduce_task_vector<R, FULL>(t, F, yF);
+		}
+
+		// ---- pass 2 over the Jacobian columns: X = L^-1 J_t^T row by row (row r needs column r of J only)
 		double X[N][R];
 #pragma unroll
-		for (int r = 0; r < N; r++)
+		for (int r = 0; r < N; r++) {
+			double c6[6], cr[R];
+			jacobian_column<N>(mdl, kd, t.body, x, r, c6);
+			reduce_task_vector<R, FULL>(t, c6, cr);
 #pragma unroll
-			for (int a = 0; a < R; a++) {
-				double s = JtT[r][a];
+			for (int k = 0; k < r; k++) {
+				const double l = Ls.L(r, k);
 #pragma unroll
-				for (int k = 0; k < r; k++) s -= L[r][k] * X[k][a];
-				X[r][a] = s * invd[r];
+				for (int a = 0; a < R; a++) cr[a] -= l * X[k][a];
 			}
-		// bounded inertia estimates: M_BIE = M + diag(h^2); with one clamped entry: M + h h^T, g = L^-1 h, z = J M^-1 h = X^T g
+			const double inv = Ls.invd(r);
+#pragma unroll
+			for (int a = 0; a < R; a++) X[r][a] = cr[a] * inv;
+		}
+		// bounded inertia estimates: M_BIE = M + diag(d); with one clamped entry: M + delta e e^T,
+		// g = L^-1 e, mu = g.g, z = J M^-1 e = X^T g
 		const int dec = p.dynamic_decoupling_type;
 		int kclamp = 0;
-		double z[R], mu = 0.0;
+		double z[R], mu = 0.0, delta = 0.0;
 		double h[N];
 		if (dec == OSC_BOUNDED_INERTIA_ESTIMATES) {
-			kclamp = bie_shift<N>(Mdiag, p.bie_threshold, h);
+			kclamp = bie_shift<N>(Mdiag, p.bie_threshold, h, delta);
 			if (kclamp == 1) {
 				double g[N];
 #pragma unroll
-				for (int j = 0; j < N; j++) g[j] = h[j];
-				solve_lower<N>(L, invd, g);
+				for (int j = 0; j < N; j++) g[j] = (h[j] > 0.0) ? 1.0 : 0.0;
+				Ls.solve_lower(g);
 #pragma unroll
 				for (int j = 0; j < N; j++) mu += g[j] * g[j];
 #pragma unroll
@@ -246,7 +273,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		if (dec == OSC_FULL_DYNAMIC_DECOUPLING || (dec == OSC_BOUNDED_INERTIA_ESTIMATES && kclamp == 0)) {
 			solve_rtr<N, R, 0>(X, rinv, yf);
 		} else if (dec == OSC_BOUNDED_INERTIA_ESTIMATES && kclamp == 1) {
-			// (A - z z^T / (1 + mu))^-1 y = A^-1 y + (A^-1 z) (z . A^-1 y) / ((1 + mu) - z . A^-1 z)
+			// (A - delta z z^T / (1 + delta mu))^-1 y = A^-1 y + (A^-1 z) (z . A^-1 y) delta / ((1 + delta mu) - delta z . A^-1 z)
 			double sz[R];
 #pragma unroll
 			for (int a = 0; a < R; a++) sz[a] = z[a];
@@ -258,23 +285,29 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				zs += z[a] * sz[a];
 				zt += z[a] * yf[a];
 			}
-			const double f = zt / ((1.0 + mu) - zs);
+			const double f = delta * zt / ((1.0 + delta * mu) - delta * zs);
 #pragma unroll
 			for (int a = 0; a < R; a++) yf[a] += sz[a] * f;
 		} else if (dec == OSC_BOUNDED_INERTIA_ESTIMATES) {
-			// general route: A_b = (L_b^-1 J^T)^T (L_b^-1 J^T)
-			double Lb[N][N], invdb[N];
-			bie_cholesky_from_factor<N>(L, h, Lb, invdb);
-			double Wb[N][R];
+			// general route (two or more clamped entries): A_b = W^T W, W = L_b^-1 J_t^T with J_t^T = L Q [R; 0]
+			double Lf[N][N], Lb[N][N], invdb[N];
 #pragma unroll
 			for (int r = 0; r < N; r++)
 #pragma unroll
-				for (int a = 0; a < R; a++) {
-					double s = JtT[r][a];
+				for (int c = 0; c <= r; c++) Lf[r][c] = Ls.L(r, c);
+			bie_cholesky_from_factor<N>(Lf, h, Lb, invdb);
+			double Wb[N][R];
 #pragma unroll
-					for (int k = 0; k < r; k++) s -= Lb[r][k] * Wb[k][a];
-					Wb[r][a] = s * invdb[r];
-				}
+			for (int a = 0; a < R; a++) {
+				double e[N], col[N];
+#pragma unroll
+				for (int j = 0; j < N; j++) e[j] = (j <= a) ? X[j][a] : 0.0;  // column a of [R; 0]
+				apply_q<N, R, 0>(X, vhead, beta, e);
+				mul_lower<N>(Lf, e, col);
+				solve_lower<N>(Lb, invdb, col);
+#pragma unroll
+				for (int j = 0; j < N; j++) Wb[j][a] = col[j];
+			}
 			double Ab[R][R], invda[R];
 #pragma unroll
 			for (int a = 0; a < R; a++)
@@ -288,12 +321,26 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			cholesky_lower<R>(Ab, invda);
 			solve_spd<R>(Ab, invda, yf);
 		}  // IMPEDANCE: Lambda_modified = I
+		// tau_task = J_t^T y = L Q [R y; 0]
+		{
+			if (has_F) {
 #pragma unroll
-		for (int j = 0; j < N; j++) {
-			double s = 0.0;
+				for (int a = 0; a < R; a++) yf[a] += yF[a];
+			}
+			double e[N], lt[N];
 #pragma unroll
-			for (int a = 0; a < R; a++) s += JtT[j][a] * (has_F ? yf[a] + yF[a] : yf[a]);
-			tau[j] += s;
+			for (int r = 0; r < N; r++) {
+				double s = 0.0;
+				if (r < R) {
+#pragma unroll
+					for (int a = r; a < R; a++) s += X[r][a] * yf[a];
+				}
+				e[r] = s;
+			}
+			apply_q<N, R, 0>(X, vhead, beta, e);
+			Ls.mul_lower(e, lt);
+#pragma unroll
+			for (int j = 0; j < N; j++) tau[j] += lt[j];
 		}
 
 		if constexpr (HAS_JT) {
@@ -304,7 +351,15 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				status |= OSC_STATUS_ZERO_RANGE;  // JointTask.cpp:234-239, 302-306
 			} else {
 				double pid[N], acc[N];
-				joint_control_law<N, N>(jt, NR, i, q, dq, pid, acc);
+				{
+					double qj[N], dqj[N];  // re-read (L2 hot) rather than kept live across the task above
+#pragma unroll
+					for (int j = 0; j < N; j++) {
+						qj[j] = P.q[(int64_t)j * NR + i];
+						dqj[j] = P.dq[(int64_t)j * NR + i];
+					}
+					joint_control_law<N, N>(jt, NR, i, qj, dqj, pid, acc);
+				}
 				// Q_perp = H_1..H_R [0; I],  W = L^-T Q_perp,  K = L Q_perp
 				double Qp[N][Mn], W[N][Mn], K[N][Mn];
 #pragma unroll
@@ -314,10 +369,10 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 					for (int j = 0; j < N; j++) e[j] = (j == R + a) ? 1.0 : 0.0;
 					apply_q<N, R, 0>(X, vhead, beta, e);
 					double k[N];
-					mul_lower<N>(L, e, k);
+					Ls.mul_lower(e, k);
 #pragma unroll
 					for (int j = 0; j < N; j++) Qp[j][a] = e[j];
-					solve_lower_t<N>(L, invd, e);
+					Ls.solve_lower_t(e);
 #pragma unroll
 					for (int j = 0; j < N; j++) {
 						W[j][a] = e[j];
@@ -347,7 +402,8 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				if (P.use_prev_torques) {
 #pragma unroll
 					for (int j = 0; j < N; j++) rhs[j] = tau[j];
-					solve_spd<N>(L, invd, rhs);
+					Ls.solve_lower(rhs);
+					Ls.solve_lower_t(rhs);
 #pragma unroll
 					for (int j = 0; j < N; j++) rhs[j] = acc[j] - rhs[j];
 				} else {
@@ -372,14 +428,15 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 					solve_spd<Mn>(G, invg, z2);
 				} else if (jdec == OSC_BOUNDED_INERTIA_ESTIMATES) {
 					solve_spd<Mn>(G, invg, z2);
-					double hj[N];
-					const int kj = bie_shift<N>(Mdiag, jp.bie_threshold, hj);
+					double hj[N], dj = 0.0;
+					const int kj = bie_shift<N>(Mdiag, jp.bie_threshold, hj, dj);
 					if (kj == 1) {
-						// H = K^T M_b^-1 K = I - c c^T / (1 + mu),  c = Q_perp^T L^-1 h;  H^-1 z = z + c (c . z) / ((1 + mu) - c . c)
+						// H = K^T M_b^-1 K = I - delta c c^T / (1 + delta mu),  c = Q_perp^T L^-1 e;
+						// H^-1 z = z + c (c . z) delta / ((1 + delta mu) - delta c . c)
 						double g[N];
 #pragma unroll
-						for (int j = 0; j < N; j++) g[j] = hj[j];
-						solve_lower<N>(L, invd, g);
+						for (int j = 0; j < N; j++) g[j] = (hj[j] > 0.0) ? 1.0 : 0.0;
+						Ls.solve_lower(g);
 						double muj = 0.0;
 #pragma unroll
 						for (int j = 0; j < N; j++) muj += g[j] * g[j];
@@ -393,12 +450,16 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 							cc += s * s;
 							cz += s * z2[a];
 						}
-						const double f = cz / ((1.0 + muj) - cc);
+						const double f = dj * cz / ((1.0 + dj * muj) - dj * cc);
 #pragma unroll
 						for (int a = 0; a < Mn; a++) z2[a] += c[a] * f;
 					} else if (kj >= 2) {
-						double Lb[N][N], invdb[N];
-						bie_cholesky_from_factor<N>(L, hj, Lb, invdb);
+						double Lf[N][N], Lb[N][N], invdb[N];
+#pragma unroll
+						for (int r = 0; r < N; r++)
+#pragma unroll
+							for (int c = 0; c <= r; c++) Lf[r][c] = Ls.L(r, c);
+						bie_cholesky_from_factor<N>(Lf, hj, Lb, invdb);
 						double Z[N][Mn];
 #pragma unroll
 						for (int a = 0; a < Mn; a++) {

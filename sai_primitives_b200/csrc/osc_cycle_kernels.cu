@@ -41,10 +41,21 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 	}
 	if (e0 != cudaSuccess) return e0;
 	if constexpr (R > 0) {
-		// the SVD path for the robots the fast kernel handed over (usually none or few: exits immediately)
+		// The general path for the robots the fast kernel handed over (usually none or few).  One block per SM,
+		// grid-stride over the compacted list; launched with programmatic stream serialization so that its launch
+		// latency overlaps the tail of the fast kernel (it waits on griddepcontrol.wait before reading the list).
 		const long long want = (P.n_robots + 63) / 64;
-		const unsigned sgrid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
-		osc_singular_kernel<N><<<sgrid, 64, 0, stream>>>(P);
+		cudaLaunchConfig_t cfg{};
+		cfg.gridDim = dim3((unsigned)(want < 148 ? want : 148));
+		cfg.blockDim = dim3(64);
+		cfg.dynamicSmemBytes = 0;
+		cfg.stream = stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr;
+		cfg.numAttrs = 1;
+		return cudaLaunchKernelEx(&cfg, osc_singular_kernel<N>, P);
 	}
 	return cudaGetLastError();
 }

@@ -150,7 +150,8 @@ DEVI void householder_qr(double (&X)[N][R], double (&vhead)[R], double (&beta)[R
 		const double v0 = x0 - alpha;
 		// v^T v = nrm2 - 2 alpha x0 + alpha^2 = 2 (nrm2 - alpha x0)
 		const double vv = 2.0 * (nrm2 - alpha * x0);
-		const double b = (vv > 0.0) ? 2.0 / vv : 0.0;
+		// beta = 2 / v^T v = 1 / (nrm (nrm + |x0|)):  one reciprocal, no division
+		const double b = (vv > 0.0) ? 2.0 * __drcp_rn(vv) : 0.0;
 		vhead[j] = v0;
 		beta[j] = b;
 #pragma unroll
@@ -249,5 +250,90 @@ DEVI bool sound_nonsingular(const double (&JT)[N][R], double thr, double abs_tol
 	double invd[R];
 	return cholesky_lower<R>(G, invd);
 }
+
+// Same sufficient test starting from the Gram matrix G = J J^T (full symmetric storage, destroyed).
+template <int R>
+DEVI bool sound_nonsingular_gram(double (&G)[R][R], double thr, double abs_tol) {
+	double tr = 0.0;
+#pragma unroll
+	for (int a = 0; a < R; a++) tr += G[a][a];
+	if (!(tr > (double)R * abs_tol * abs_tol)) return false;
+	if (R == 1) return true;
+	double G2[R][R];
+#pragma unroll
+	for (int a = 0; a < R; a++)
+#pragma unroll
+		for (int b = 0; b <= a; b++) {
+			double s = 0.0;
+#pragma unroll
+			for (int i = 0; i < R; i++) s += G[a][i] * G[i][b];
+			G2[a][b] = s;
+			G2[b][a] = s;
+		}
+	double t8 = 0.0;  // tr(G^8) = ||G^4||_F^2,  G^4 = G2*G2
+#pragma unroll
+	for (int a = 0; a < R; a++)
+#pragma unroll
+		for (int b = 0; b <= a; b++) {
+			double s = 0.0;
+#pragma unroll
+			for (int i = 0; i < R; i++) s += G2[a][i] * G2[i][b];
+			t8 += (a == b) ? s * s : 2.0 * s * s;
+		}
+	const double hi = sqrt(sqrt(sqrt(t8)));
+	const double shift = thr * thr * hi;
+#pragma unroll
+	for (int a = 0; a < R; a++) G[a][a] -= shift;
+	double invd[R];
+	return cholesky_lower<R>(G, invd);
+}
+
+// ---- lower-triangular factor staged in shared memory: element (r, c) of this thread's matrix at
+// b[(r (r + 1) / 2 + c) * STRIDE], the reciprocal diagonal behind it.  STRIDE is the (compile-time) block size, so
+// every address is base + constant.
+template <int N, int STRIDE>
+struct SmTri {
+	double* b;
+	DEVI double L(int r, int c) const { return b[(r * (r + 1) / 2 + c) * STRIDE]; }
+	DEVI double invd(int r) const { return b[(N * (N + 1) / 2 + r) * STRIDE]; }
+	DEVI void store(const double (&A)[N][N], const double (&inv)[N]) {
+#pragma unroll
+		for (int r = 0; r < N; r++) {
+#pragma unroll
+			for (int c = 0; c <= r; c++) b[(r * (r + 1) / 2 + c) * STRIDE] = A[r][c];
+			b[(N * (N + 1) / 2 + r) * STRIDE] = inv[r];
+		}
+	}
+	// x <- L^-1 x
+	DEVI void solve_lower(double (&x)[N]) const {
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			double s = x[i];
+#pragma unroll
+			for (int k = 0; k < i; k++) s -= L(i, k) * x[k];
+			x[i] = s * invd(i);
+		}
+	}
+	// x <- L^-T x
+	DEVI void solve_lower_t(double (&x)[N]) const {
+#pragma unroll
+		for (int i = N - 1; i >= 0; i--) {
+			double s = x[i];
+#pragma unroll
+			for (int k = i + 1; k < N; k++) s -= L(k, i) * x[k];
+			x[i] = s * invd(i);
+		}
+	}
+	// y = L x
+	DEVI void mul_lower(const double (&x)[N], double (&y)[N]) const {
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			double s = 0.0;
+#pragma unroll
+			for (int k = 0; k <= i; k++) s += L(i, k) * x[k];
+			y[i] = s;
+		}
+	}
+};
 
 }  // namespace osc

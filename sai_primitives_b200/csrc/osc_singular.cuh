@@ -572,6 +572,8 @@ static __device__ __noinline__ void generic_cycle_one(const OscProgram& P, const
 // Fixed grid, grid-stride over the list: with an empty list every thread exits at once.
 template <int N>
 __global__ void __launch_bounds__(64) osc_singular_kernel(const __grid_constant__ OscProgram P) {
+	// programmatic dependent launch: wait until the fast kernel of this cycle has completed and flushed its writes
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 	const int32_t count = P.sing_count[P.sing_parity];
 	const int stride = gridDim.x * blockDim.x;
 	for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < count; slot += stride)
