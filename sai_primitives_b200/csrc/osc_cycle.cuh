@@ -69,6 +69,8 @@ DEVI void bie_cholesky_from_factor(const double (&L)[N][N], const double (&d)[N]
 	cholesky_lower<N>(Lb, invdb);
 }
 
+DEVI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // y = B^T v: the six world-frame components of a task vector reduced to the R coordinates of the task range
 // (identity for a full task)
 template <int R, bool FULL>
@@ -107,6 +109,28 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		q[j] = P.q[(int64_t)j * NR + i];
 		dq[j] = P.dq[(int64_t)j * NR + i];
 	}
+	// Warm L2/L1 with this robot's task state (goals, integrators) while the kinematics run: with two warps per
+	// scheduler a first-touch DRAM miss in the middle of the control law cannot be hidden otherwise.
+#ifndef OSC_NO_PREFETCH
+	if constexpr (R > 0) {
+		const DevMft& t = P.mft[0];
+#pragma unroll
+		for (int c = 0; c < 24; c++) prefetch_l2(t.st + (int64_t)c * NR + i);
+#pragma unroll
+		for (int c = 0; c < 6; c++) prefetch_l2(t.st + (int64_t)(MC_INT_POS + c) * NR + i);
+		prefetch_l2(t.ist + (int64_t)MI_N_TYPES * NR + i);
+	}
+	if constexpr (HAS_JT || R == 0) {
+		const DevJt& jt = P.jt[0];
+#pragma unroll
+		for (int c = 0; c < N; c++) {
+			prefetch_l2(jt.st + (int64_t)(JC_GOAL_POS + c) * NR + i);
+			prefetch_l2(jt.st + (int64_t)(JC_GOAL_VEL + c) * NR + i);
+			prefetch_l2(jt.st + (int64_t)(JC_GOAL_ACC + c) * NR + i);
+			prefetch_l2(jt.st + (int64_t)(JC_INT + c) * NR + i);
+		}
+	}
+#endif
 	KinDynS<N> kd;
 	forward_kinematics_s<N>(mdl, q, kd, smt, sms);
 

@@ -362,3 +362,139 @@ def test_config4_mixed_dof_batch():
             assert np.abs(a[i] - b[i]).max() <= REL_TOL * max(np.abs(b[i]).max(), 1e-9), (cycle, i, models[i])
         q = [qi + 0.002 * dqi for qi, dqi in zip(q, dq)]
         gpu.set_state(q, dq); ora.set_state(q, dq)
+
+
+def test_config3_surface_contact_moment_control_in_compliant_frame():
+    """BASELINE config 3, second variant (examples/07-surface_surface_contact/...cpp:135-201): full 6-DoF task with the
+    force/motion spaces parametrised in the compliant frame, force space dim 1 + moment space dim 2 about local Z,
+    closed-loop force (with passivity) and closed-loop moment, custom force/moment gains, sensor frame set,
+    MotionForceTask alone in the controller; 120 cycles with a moving state and noisy sensed wrench."""
+    import sai_primitives_b200 as sp
+    N = 24
+    K = 120
+    q, dq, _ = sample_states("panda", N, min_sigma_ratio=0.08)
+    link, pt = TASK_POINTS["panda"]
+    comp = (np.eye(3), np.array(pt))
+    robot = sp.BatchedRobot("panda", N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    mft = sp.MotionForceTask(robot, link, comp, task_name="surface_alignment_task",
+                             is_force_motion_parametrization_in_compliant_frame=True)
+    mft.enablePassivity()
+    sensor_R = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]]); sensor_t = np.array([0.01, 0.02, 0.05])
+    mft.setForceSensorFrame(link, (sensor_R, sensor_t))
+    ctrl = sp.RobotController(robot, [mft])
+    ob = OracleBatch("panda", N); ob.set_state(q, dq)
+    omft = ob.add_mft(link, comp, in_compliant=True, name="surface_alignment_task"); ob.finalize()
+    for t in omft:
+        t.enablePassivity(); t.setForceSensorFrame(link, (sensor_R, sensor_t))
+    _set_mft_goals(mft, omft, N)
+
+    def sensed(k):
+        f = np.zeros((N, 3)); m = np.zeros((N, 3))
+        for i in range(N):
+            g = rng_for(i * 7919 + k, stream=8)
+            f[i] = np.array([0.3, -0.2, 9.0]) + g.normal(0, 1.5, 3); m[i] = g.normal(0, 0.3, 3)
+        return f, m
+
+    for k in range(K):
+        if k == 5:   # contact detected: switch spaces, close the loops (examples/07:188-201)
+            assert mft.parametrizeForceMotionSpaces(1, (0, 0, 1)) is True
+            assert mft.parametrizeMomentRotMotionSpaces(2, (0, 0, 1)) is True
+            mft.setClosedLoopForceControl(); mft.setClosedLoopMomentControl()
+            mft.setGoalForce(np.array([0, 0, 10.0])); mft.setGoalMoment(np.zeros(3))
+            mft.setForceControlGains(0.7, 5.0, 1.5); mft.setMomentControlGains(0.7, 4.0, 1.5)
+            for t in omft:
+                t.parametrizeForceMotionSpaces(1, (0, 0, 1)); t.parametrizeMomentRotMotionSpaces(2, (0, 0, 1))
+                t.setClosedLoopForceControl(); t.setClosedLoopMomentControl()
+                t.setGoalForce((0, 0, 10.0)); t.setGoalMoment((0, 0, 0))
+                t.setForceControlGains(0.7, 5.0, 1.5); t.setMomentControlGains(0.7, 4.0, 1.5)
+        f, m = sensed(k)
+        mft.updateSensedForceAndMoment(f, m)
+        for i in range(N):
+            omft[i].updateSensedForceAndMoment(f[i], m[i])
+        ctrl.updateControllerTaskModels()
+        tau = ctrl.computeControlTorques()
+        ref = ob.cycle()
+        assert (robot.status() & sp.capi.STATUS_UNHANDLED).sum() == 0
+        assert rel_err(tau, ref).max() < REL_TOL, k
+        q = q + 0.001 * dq
+        robot.setQ(q); robot.updateModel(); ob.set_state(q, dq)
+    sf = mft.getSensedForceControlWorldFrame()
+    assert np.abs(sf - np.array([t._sensed_force_control_world_frame for t in omft])).max() < 1e-12
+
+
+def test_velocity_saturation_and_anisotropic_gains():
+    """Velocity saturation in both tasks (MotionForceTask.cpp:416-461, JointTask.cpp:327-340) and per-axis gains."""
+    import sai_primitives_b200 as sp
+    N = 48
+    q, dq, _ = sample_states("panda", N, min_sigma_ratio=0.08)
+    link, pt = TASK_POINTS["panda"]
+    robot = sp.BatchedRobot("panda", N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    mft = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt)))
+    jt = sp.JointTask(robot)
+    mft.enableVelocitySaturation(0.05, 0.2); mft.setPosControlGains([100, 150, 80], [20, 25, 15], [2, 0, 1]); mft.setOriControlGains(150, 25, 3)
+    jt.enableVelocitySaturation(0.3); jt.setGains(np.linspace(40, 70, 7), np.linspace(10, 16, 7), np.linspace(0, 3, 7))
+    ctrl = sp.RobotController(robot, [mft, jt])
+    ob = OracleBatch("panda", N); ob.set_state(q, dq)
+    omft = ob.add_mft(link, (np.eye(3), np.array(pt))); ojt = ob.add_jt(); ob.finalize()
+    for a, b in zip(omft, ojt):
+        a.enableVelocitySaturation(0.05, 0.2); a.setPosControlGains([100, 150, 80], [20, 25, 15], [2, 0, 1]); a.setOriControlGains(150, 25, 3)
+        b.enableVelocitySaturation(0.3); b.setGains(np.linspace(40, 70, 7), np.linspace(10, 16, 7), np.linspace(0, 3, 7))
+    _set_mft_goals(mft, omft, N); _set_joint_goals(jt, ojt, q, 7, with_vel=True)
+    for cycle in range(3):
+        ctrl.updateControllerTaskModels()
+        assert rel_err(ctrl.computeControlTorques(), ob.cycle()).max() < REL_TOL
+    with pytest.raises(ValueError):
+        mft.setPosControlGains(-1.0, 20.0)          # MotionForceTask.cpp:583-587
+    with pytest.raises(ValueError):
+        jt.enableVelocitySaturation(-0.1)             # JointTask.cpp:409-413
+    with pytest.raises(NotImplementedError):
+        jt.enableInternalOtgAccelerationLimited(1.0, 2.0)
+
+
+def test_full_size_properties_262144_robots():
+    """BASELINE config 3 size (262,144 robots): size-independent properties instead of an oracle loop --
+    (i) the batch result equals the same robots evaluated in shuffled order and in chunks (no cross-robot coupling,
+    no dependence on the batch index), (ii) duplicated robots get bit-identical torques, (iii) an 8,192-robot
+    sample matches the C++ oracle."""
+    import sai_primitives_b200 as sp
+    from oracle.cpp_ref import CppOracleBatch
+    N = 262144
+    base_q, base_dq, _ = sample_states("panda", 2048, min_sigma_ratio=0.075)
+    rng = np.random.default_rng(77)
+    pick = rng.integers(0, 2048, N)
+    q, dq = base_q[pick], base_dq[pick]
+    link, pt = TASK_POINTS["panda"]
+
+    def run(qs, dqs):
+        robot = sp.BatchedRobot("panda", qs.shape[0])
+        robot.setQ(qs); robot.setDq(dqs); robot.updateModel()
+        mft = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt))); jt = sp.JointTask(robot)
+        ctrl = sp.RobotController(robot, [mft, jt])
+        mft.setGoalLinearVelocity(np.array([0.02, -0.01, 0.03])); jt.setGoalPosition(qs + 0.05)
+        ctrl.updateControllerTaskModels()
+        tau = ctrl.computeControlTorques()
+        st = robot.status()
+        robot.close()
+        return tau, st
+    tau, st = run(q, dq)
+    assert (st & sp.capi.STATUS_UNHANDLED).sum() == 0 and np.isfinite(tau).all()
+    # (ii) duplicates are bit-identical
+    first = {}
+    for i in range(0, N, 997):
+        first.setdefault(int(pick[i]), i)
+        assert np.array_equal(tau[i], tau[first[int(pick[i])]])
+    # (i) shuffled order
+    perm = rng.permutation(N)
+    tau_p, _ = run(q[perm], dq[perm])
+    assert np.array_equal(tau_p, tau[perm])
+    # (iii) sample against the C++ oracle
+    idx = np.arange(0, N, 32)
+    cb = CppOracleBatch("panda", idx.size); cb.set_state(q[idx], dq[idx])
+    tm = cb.add_mft(link, (np.eye(3), np.array(pt))); tj = cb.add_jt()
+    x0, R0 = cb.mft_get_current(tm)
+    z = np.zeros((idx.size, 3))
+    cb.mft_set_goals(tm, x0, R0, np.tile([0.02, -0.01, 0.03], (idx.size, 1)), z, z, z); cb.jt_set_goals(tj, q[idx] + 0.05)
+    ref = cb.cycle(n_threads=8)
+    assert rel_err(tau[idx], ref).max() < REL_TOL
