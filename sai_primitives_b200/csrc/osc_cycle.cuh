@@ -95,10 +95,13 @@ DEVI void reduce_task_vector(const DevMft& t, const double (&v6)[6], double (&y)
 template <int N, int R, bool HAS_JT, bool FULL>
 __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(const __grid_constant__ OscProgram P) {
 	extern __shared__ double sm[];
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int64_t NR = P.n_robots;
-	if (i == 0 && P.sing_count) P.sing_count[P.sing_parity ^ 1] = 0;
-	if (i >= NR) return;
+	const int64_t i_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i_raw == 0 && P.sing_count) P.sing_count[P.sing_parity ^ 1] = 0;
+	// Every thread of the block walks the whole kernel (the phase barriers below need all of them): threads past the
+	// end of the batch and robots handed to the general path keep computing on valid data but touch no state.
+	bool alive = i_raw < NR;
+	const int64_t i = alive ? i_raw : NR - 1;
 	const DevModel& mdl = P.model;
 	double* smt = sm + threadIdx.x;
 	constexpr int sms = kCycleBlock;  // the launcher always uses kCycleBlock threads per block
@@ -148,7 +151,9 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		const DevJt& t = P.jt[0];
 		const osc_joint_params& p = t.p;
 		double pid[N], acc[N];
-		joint_control_law<N, N>(t, NR, i, q, dq, pid, acc);
+#pragma unroll
+		for (int j = 0; j < N; j++) pid[j] = acc[j] = 0.0;
+		if (alive) joint_control_law<N, N>(t, NR, i, q, dq, pid, acc);
 #pragma unroll
 		for (int r = 0; r < N; r++) {
 			double s = 0.0;
@@ -194,6 +199,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				for (int a = 0; a < R; a++)
 #pragma unroll
 					for (int b = 0; b <= a; b++) G[a][b] += cr[a] * cr[b];
+				OSC_LS();
 			}
 #pragma unroll
 			for (int a = 0; a < R; a++)
@@ -202,9 +208,8 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			// Branch decision of SingularityHandler::updateTaskModel (:83-105), taken before any task state is touched and
 			// before the dynamics are evaluated: robots that are not provably non-singular are appended
 			// (warp-aggregated) to the list of the general-path kernel and leave this kernel.
-			const bool flagged = !sound_nonsingular_gram<R>(G, p.s_max, p.s_abs_tol);
-			const unsigned act = __activemask();
-			const unsigned m = __ballot_sync(act, flagged);
+			const bool flagged = alive && !sound_nonsingular_gram<R>(G, p.s_max, p.s_abs_tol);
+			const unsigned m = __ballot_sync(0xffffffffu, flagged);
 			if (flagged) {
 				const int lane = threadIdx.x & 31;
 				const int leader = __ffs(m) - 1;
@@ -212,12 +217,12 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				if (lane == leader) base = atomicAdd(&P.sing_count[P.sing_parity], __popc(m));
 				base = __shfl_sync(m, base, leader);
 				P.sing_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
-				return;
+				alive = false;	// the general-path kernel owns this robot from here on
 			}
 		}
 		// classifySingularity with an empty singular range clears the handler memory (:239-245); only robots that
 		// were singular at the previous update have anything to clear
-		if (P.update_models && t.ist[(int64_t)MI_N_TYPES * NR + i] != 0) {
+		if (alive && P.update_models && t.ist[(int64_t)MI_N_TYPES * NR + i] != 0) {
 			t.ist[(int64_t)MI_N_TYPES * NR + i] = 0;
 			t.ist[(int64_t)MI_T1_COUNTER * NR + i] = 0;
 			t.ist[(int64_t)MI_T2_COUNTER * NR + i] = 0;
@@ -241,11 +246,13 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			Ls.store(kd.M, invd);
 		}
 
+		OSC_LS();
 		double yf[R], yF[R];
 		bool has_F;
 		{
-			double fstar[6], F[6];
-			has_F = mft_control_law(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status);
+			double fstar[6] = {0, 0, 0, 0, 0, 0}, F[6] = {0, 0, 0, 0, 0, 0};
+			has_F = true;
+			if (alive) has_F = mft_control_law(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status);
 			reduce_task_vector<R, FULL>(t, fstar, yf);
 			reduce_task_vector<R, FULL>(t, F, yF);
 		}
@@ -266,6 +273,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			const double inv = Ls.invd(r);
 #pragma unroll
 			for (int a = 0; a < R; a++) X[r][a] = cr[a] * inv;
+			OSC_LS();
 		}
 		// bounded inertia estimates: M_BIE = M + diag(d); with one clamped entry: M + delta e e^T,
 		// g = L^-1 e, mu = g.g, z = J M^-1 e = X^T g
@@ -291,8 +299,10 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				}
 			}
 		}
+		OSC_LS();
 		double vhead[R], beta[R], rinv[R];
 		householder_qr<N, R, 0>(X, vhead, beta, rinv);
+		OSC_LS();
 
 		if (dec == OSC_FULL_DYNAMIC_DECOUPLING || (dec == OSC_BOUNDED_INERTIA_ESTIMATES && kclamp == 0)) {
 			solve_rtr<N, R, 0>(X, rinv, yf);
@@ -345,6 +355,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			cholesky_lower<R>(Ab, invda);
 			solve_spd<R>(Ab, invda, yf);
 		}  // IMPEDANCE: Lambda_modified = I
+		OSC_LS();
 		// tau_task = J_t^T y = L Q [R y; 0]
 		{
 			if (has_F) {
@@ -375,7 +386,9 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				status |= OSC_STATUS_ZERO_RANGE;  // JointTask.cpp:234-239, 302-306
 			} else {
 				double pid[N], acc[N];
-				{
+#pragma unroll
+				for (int j = 0; j < N; j++) pid[j] = acc[j] = 0.0;
+				if (alive) {
 					double qj[N], dqj[N];  // re-read (L2 hot) rather than kept live across the task above
 #pragma unroll
 					for (int j = 0; j < N; j++) {
@@ -384,6 +397,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 					}
 					joint_control_law<N, N>(jt, NR, i, qj, dqj, pid, acc);
 				}
+		OSC_LS();
 				// Q_perp = H_1..H_R [0; I],  W = L^-T Q_perp,  K = L Q_perp
 				double Qp[N][Mn], W[N][Mn], K[N][Mn];
 #pragma unroll
@@ -421,6 +435,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				// ||N_prec||_F^2 = tr(G K^T K) must stay < 1e6 for the reference's 1e-3 range tolerance
 				if (!(nrm_chk < 1.0e6)) status |= OSC_STATUS_UNHANDLED;
 				cholesky_lower<Mn>(G, invg);
+		OSC_LS();
 				// u = W^T (qdd_d - M^-1 tau_prec)
 				double rhs[N];
 				if (P.use_prev_torques) {
@@ -537,9 +552,11 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 #pragma unroll
 		for (int j = 0; j < N; j++) tau[j] = __longlong_as_double(0x7ff8000000000000LL);
 	}
+	if (alive) {
 #pragma unroll
-	for (int j = 0; j < N; j++) P.tau[(int64_t)j * NR + i] = tau[j];
-	P.status[i] = status;
+		for (int j = 0; j < N; j++) P.tau[(int64_t)j * NR + i] = tau[j];
+		P.status[i] = status;
+	}
 }
 
 }  // namespace osc
