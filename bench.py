@@ -252,7 +252,7 @@ def gpu_arm(args):
     global SEED
     SEED = 1234 + rank
     t_gen = time.time()
-    q, dq, rejected, rng = sample_batch(sp, R, local_rank)
+    q, dq, rejected, rng = sample_batch(sp, R, local_rank, min_ratio=args.min_ratio)
     log("[rank %d] sampled %d non-singular states (rejected fraction %.3f) in %.1fs" % (rank, R, rejected, time.time() - t_gen))
 
     # a dedicated (non-default) stream shared by torch and the library, so that torch.cuda.Event timing sees the kernels
@@ -319,6 +319,7 @@ def gpu_arm(args):
     # parity guard on the timed data: every robot stayed on the fast path and the torques are finite
     st = sets[0]["robot"].status()
     tau_host = sets[0]["tau"].cpu().numpy()
+    singular_fraction = float(((st & capi.STATUS_SINGULAR_PATH) != 0).mean())
     if (st & capi.STATUS_UNHANDLED).any() or not np.isfinite(tau_host).all():
         raise SystemExit("bench: robots left the CUDA fast path (%d unhandled)" % int(((st & capi.STATUS_UNHANDLED) != 0).sum()))
 
@@ -384,7 +385,7 @@ def gpu_arm(args):
                                    "BIE decoupling (reference defaults)",
                        "robots_per_gpu": R, "robots_total": R * world,
                        "l2": "inputs larger than L2: %d controller instances (%.0f MB of state) used round-robin" % (n_sets, n_sets * R * 8 * 250 / 1e6),
-                       "state_filter": "s_min/s_max >= 0.1 (non-singular branch), rejected fraction %.3f" % rejected,
+                       "state_filter": "s_min/s_max >= %.3g, rejected fraction %.3f; robots on the general (SVD) path: %.4f" % (args.min_ratio, rejected, singular_fraction),
                        "parallelism": "robots sharded by batch index, %d process(es), no collective" % world},
             "latency_ms": {"p50": float(np.percentile(per_step_ms, 50)), "p99": float(np.percentile(per_step_ms, 99)),
                            "max": float(per_step_ms.max()), "samples": int(per_step_ms.size), "what": "CUDA events around one batched cycle, rank 0"},
@@ -424,6 +425,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--min-ratio", type=float, default=0.1, help="reject states with s_min/s_max below this (0: unfiltered, about half of the Panda states then take the singular branch)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

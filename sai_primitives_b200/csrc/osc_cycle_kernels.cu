@@ -2,6 +2,7 @@
 // so that nvcc compiles them in parallel.
 #include "osc_cycle.cuh"
 #include "osc_singular.cuh"
+#include "osc_blend.cuh"
 #include "osc_launch.h"
 
 #ifndef OSC_INST_N
@@ -46,7 +47,7 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 		// latency overlaps the tail of the fast kernel (it waits on griddepcontrol.wait before reading the list).
 		const long long want = (P.n_robots + 63) / 64;
 		cudaLaunchConfig_t cfg{};
-		cfg.gridDim = dim3((unsigned)(want < 148 ? want : 148));
+		cfg.gridDim = dim3((unsigned)(want < 148 * OSC_GENERIC_MIN_BLOCKS ? want : 148 * OSC_GENERIC_MIN_BLOCKS));
 		cfg.blockDim = dim3(64);
 		cfg.dynamicSmemBytes = 0;
 		cfg.stream = stream;
@@ -55,6 +56,10 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 		attr[0].val.programmaticStreamSerializationAllowed = 1;
 		cfg.attrs = attr;
 		cfg.numAttrs = 1;
+		if constexpr (R == 6) {
+			// flagship hierarchy: unrolled blending path (osc_blend.cuh), general path only as its fallback
+			if (P.mft[0].full) return cudaLaunchKernelEx(&cfg, osc_blend_kernel<N, JT>, P);
+		}
 		return cudaLaunchKernelEx(&cfg, osc_singular_kernel<N>, P);
 	}
 	return cudaGetLastError();

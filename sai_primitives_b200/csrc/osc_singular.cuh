@@ -11,6 +11,10 @@
 #include "osc_kindyn.cuh"
 #include "osc_tasks.cuh"
 
+#ifndef OSC_GENERIC_MIN_BLOCKS
+#define OSC_GENERIC_MIN_BLOCKS 4
+#endif
+
 namespace osc {
 namespace sg {
 
@@ -571,7 +575,7 @@ static __device__ __noinline__ void generic_cycle_one(const OscProgram& P, const
 // SVD-path kernel: the robots in `sing_list` (count on the device, written by the fast kernel of the same cycle).
 // Fixed grid, grid-stride over the list: with an empty list every thread exits at once.
 template <int N>
-__global__ void __launch_bounds__(64) osc_singular_kernel(const __grid_constant__ OscProgram P) {
+__global__ void __launch_bounds__(64, OSC_GENERIC_MIN_BLOCKS) osc_singular_kernel(const __grid_constant__ OscProgram P) {
 	// programmatic dependent launch: wait until the fast kernel of this cycle has completed and flushed its writes
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 	const int32_t count = P.sing_count[P.sing_parity];
@@ -583,7 +587,7 @@ __global__ void __launch_bounds__(64) osc_singular_kernel(const __grid_constant_
 // Whole-batch kernel for hierarchies without a specialised fast kernel (partial joint tasks, several motion-force
 // tasks, ...): every robot takes the general path.
 template <int N>
-__global__ void __launch_bounds__(64) osc_generic_kernel(const __grid_constant__ OscProgram P) {
+__global__ void __launch_bounds__(64, OSC_GENERIC_MIN_BLOCKS) osc_generic_kernel(const __grid_constant__ OscProgram P) {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= P.n_robots) return;
 	generic_cycle_one<N>(P, i, 0u);
