@@ -36,13 +36,14 @@ DEVI void jacobi_eig6(double (&G)[6][6], double (&U)[6][6]) {
 #pragma unroll
 			for (int b = 0; b < a; b++) off += G[a][b] * G[a][b];
 		}
-		if (off <= 1e-34 * dia) break;
+		// off-diagonal entries at 1e-15 of the diagonal scale: the rounding floor of the rotations is ~1e-16
+		if (off <= 1e-30 * dia) break;
 #pragma unroll
 		for (int p = 0; p < 5; p++)
 #pragma unroll
 			for (int q = p + 1; q < 6; q++) {
 				const double gpq = G[p][q];
-				if (fabs(gpq) > 1e-300) {
+				if (fabs(gpq) > 1e-18 * (fabs(G[p][p]) + fabs(G[q][q]))) {
 					const double theta = (G[q][q] - G[p][p]) / (2.0 * gpq);
 					const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
 					const double c = rsqrt(t * t + 1.0), s = t * c;
@@ -182,6 +183,38 @@ DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const
 		}
 	}
 
+	// task velocity J0 dq (the Jacobian is not needed after this point)
+	double v[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+#pragma unroll
+	for (int j = 0; j < N; j++)
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			v[k] += JT0[j][k] * dq[j];
+			w[k] += JT0[j][3 + k] * dq[j];
+		}
+	// ---- T = X U (its Householder QR follows below; X is not needed after this point)
+	double T[N][6];
+#pragma unroll
+	for (int r = 0; r < N; r++)
+#pragma unroll
+		for (int c = 0; c < 6; c++) {
+			double s = 0.0;
+#pragma unroll
+			for (int a = 0; a < 6; a++) s += Xw[r][a] * Ue[a][c];
+			T[r][c] = s;
+		}
+	// z = (X U)^T g for the bounded-inertia rank-one update, before T is overwritten
+	double zu[6];
+#pragma unroll
+	for (int c = 0; c < 6; c++) {
+		double s = 0.0;
+		if (sm) {
+#pragma unroll
+			for (int r = 0; r < N; r++) s += T[r][c] * g[r];
+		}
+		zu[c] = s;
+	}
+
 	// ---- classifySingularity (:230-295): memory of the handler
 	int32_t c1 = ist[(int64_t)MI_T1_COUNTER * NR + i], c2 = ist[(int64_t)MI_T2_COUNTER * NR + i];
 	const int32_t n_types_prev = ist[(int64_t)MI_N_TYPES * NR + i];
@@ -212,10 +245,8 @@ DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const
 			double qq[N];
 #pragma unroll
 			for (int j = 0; j < N; j++) qq[j] = q[j] + p.perturb_step_size * Vs[j][c];
-			KinDyn<N> kp;
-			forward_kinematics<N>(mdl, qq, kp);
 			double xp[3], Rp[9], dphi[3];
-			frame_pose<N>(kp, t.body, t.ctrl_R, t.ctrl_t, xp, Rp);
+			pose_only<N>(mdl, qq, t.body, t.ctrl_R, t.ctrl_t, xp, Rp);
 			orientation_error(Rp, Rc, dphi);
 			double mot = 0.0;
 #pragma unroll
@@ -256,39 +287,9 @@ DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const
 	if constexpr (NS > 0) status |= OSC_STATUS_SINGULAR_PATH;
 
 	// ---- control law (state update happens exactly once, here)
-	double v[3] = {0, 0, 0}, w[3] = {0, 0, 0};
-#pragma unroll
-	for (int j = 0; j < N; j++)
-#pragma unroll
-		for (int k = 0; k < 3; k++) {
-			v[k] += JT0[j][k] * dq[j];
-			w[k] += JT0[j][3 + k] * dq[j];
-		}
 	double fstar[6], F[6];
 	mft_control_law(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status);
 
-	// ---- X U = Q R'
-	double T[N][6];
-#pragma unroll
-	for (int r = 0; r < N; r++)
-#pragma unroll
-		for (int c = 0; c < 6; c++) {
-			double s = 0.0;
-#pragma unroll
-			for (int a = 0; a < 6; a++) s += Xw[r][a] * Ue[a][c];
-			T[r][c] = s;
-		}
-	// z = (X U)^T g for the bounded-inertia rank-one update, before T is overwritten
-	double zu[6];
-#pragma unroll
-	for (int c = 0; c < 6; c++) {
-		double s = 0.0;
-		if (sm) {
-#pragma unroll
-			for (int r = 0; r < N; r++) s += T[r][c] * g[r];
-		}
-		zu[c] = s;
-	}
 	double vhead[6], beta[6], rinv[6];
 	householder_qr<N, 6, 0>(T, vhead, beta, rinv);
 

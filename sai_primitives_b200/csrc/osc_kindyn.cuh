@@ -438,4 +438,45 @@ DEVI void jacobian_column(const DevModel& m, const KinDynS<N>& kd, int body, con
 	}
 }
 
+// Pose of a frame fixed to body `body` for joint positions q, without keeping any per-joint data (used by the
+// singularity classification, which only needs the perturbed end pose: SingularityHandler.cpp:255-260).
+template <int N>
+DEVI void pose_only(const DevModel& m, const double (&q)[N], int body, const double Rf[9], const double tf[3], double x[3], double Rout[9]) {
+	double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+	double p[3] = {0, 0, 0};
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		if (i <= body) {
+			double t[3];
+			mat3_vec(R, m.t_fix[i], t);
+			p[0] += t[0];
+			p[1] += t[1];
+			p[2] += t[2];
+			double Rn[9];
+			mat3_mul(R, m.R_fix[i], Rn);
+			if (m.jtype[i] == 0) {
+				double s, c;
+				sincos(q[i], &s, &c);
+				double Rq[9];
+				axis_angle(m.axis[i], s, c, Rq);
+				mat3_mul(Rn, Rq, R);
+			} else {
+				double a[3];
+#pragma unroll
+				for (int k = 0; k < 9; k++) R[k] = Rn[k];
+				mat3_vec(R, m.axis[i], a);
+				p[0] += a[0] * q[i];
+				p[1] += a[1] * q[i];
+				p[2] += a[2] * q[i];
+			}
+		}
+	}
+	double t[3];
+	mat3_vec(R, tf, t);
+	x[0] = p[0] + t[0];
+	x[1] = p[1] + t[1];
+	x[2] = p[2] + t[2];
+	mat3_mul(R, Rf, Rout);
+}
+
 }  // namespace osc
