@@ -69,6 +69,16 @@ DEVI void bie_cholesky_from_factor(const double (&L)[N][N], const double (&d)[N]
 	cholesky_lower<N>(Lb, invdb);
 }
 
+// Dynamic shared memory of the fused kernel, in doubles per thread: the body orientations (9 N) between the forward
+// pass and the mass matrix, then the Cholesky factor with its reciprocal diagonal (kSmFactor) followed by the N x R
+// reduced Jacobian columns and the gravity vector.
+template <int N>
+constexpr int kSmFactor = N * (N + 1) / 2 + N;
+template <int N, int R>
+constexpr int cycle_smem_doubles() {
+	return (9 * N > kSmFactor<N> + N * R + N) ? 9 * N : kSmFactor<N> + N * R + N;
+}
+
 DEVI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // y = B^T v: the six world-frame components of a task vector reduced to the R coordinates of the task range
@@ -90,11 +100,22 @@ DEVI void reduce_task_vector(const DevMft& t, const double (&v6)[6], double (&y)
 
 // Signature <N, R, HAS_JT, FULL>:  R = rank of a leading MotionForceTask (0: none), FULL = that task controls all six
 // directions (B = I), HAS_JT = a full JointTask closes the hierarchy.
-// Dynamic shared memory: 9 N doubles per thread (body orientations between the two kinematics passes),
+// Dynamic shared memory: cycle_smem_doubles<N, R>() doubles per thread,
 // element e of thread t at  sm[e * blockDim.x + t]  (conflict-free, 8-byte interleave).
-template <int N, int R, bool HAS_JT, bool FULL>
+//
+// SPEC = true is the specialisation for the default configuration of the flagship hierarchy (cycle_spec_eligible()
+// in osc_launch.h states the conditions: every joint revolute about its local z axis, pure motion control, no velocity
+// saturation, no gravity compensation, FULL or BOUNDED_INERTIA decoupling).  Everything those conditions rule out is
+// compiled out, which brings the kernel from 223 KB to under 128 KB of code: beyond that size the instruction stream
+// no longer stays in the SM's instruction cache between blocks and every 256-byte line costs a round trip to L2
+// (profiles/r01_ifetch.md).  Robots whose bounded-inertia update has rank two or more leave through the general path.
+template <int N, int R, bool HAS_JT, bool FULL, bool SPEC = false>
 __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(const __grid_constant__ OscProgram P) {
 	extern __shared__ double sm[];
+#if defined(OSC_TRACE)
+	if (threadIdx.x == 0) s_trace_k = 0;
+	OSC_LS();
+#endif
 	const int64_t NR = P.n_robots;
 	const int64_t i_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i_raw == 0 && P.sing_count) P.sing_count[P.sing_parity ^ 1] = 0;
@@ -102,16 +123,26 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	// end of the batch and robots handed to the general path keep computing on valid data but touch no state.
 	bool alive = i_raw < NR;
 	const int64_t i = alive ? i_raw : NR - 1;
+#if defined(OSC_MODEL_IN_SMEM)
+	// Model constants from shared memory (broadcast LDS into ordinary registers, freely hoisted by the scheduler)
+	// instead of the constant bank (LDCU into the few uniform registers, consumed in place).
+	__shared__ __align__(16) unsigned char s_model[sizeof(DevModel)];
+	{
+		const int4* src = reinterpret_cast<const int4*>(&P.model);
+		int4* dst = reinterpret_cast<int4*>(s_model);
+		for (int k = threadIdx.x; k < (int)(sizeof(DevModel) / sizeof(int4)); k += blockDim.x) dst[k] = src[k];
+		__syncthreads();
+	}
+	const DevModel& mdl = *reinterpret_cast<const DevModel*>(s_model);
+#else
 	const DevModel& mdl = P.model;
+#endif
 	double* smt = sm + threadIdx.x;
 	constexpr int sms = kCycleBlock;  // the launcher always uses kCycleBlock threads per block
 
-	double q[N], dq[N];
+	double q[N];
 #pragma unroll
-	for (int j = 0; j < N; j++) {
-		q[j] = P.q[(int64_t)j * NR + i];
-		dq[j] = P.dq[(int64_t)j * NR + i];
-	}
+	for (int j = 0; j < N; j++) q[j] = P.q[(int64_t)j * NR + i];
 	// Warm L2/L1 with this robot's task state (goals, integrators) while the kinematics run: with two warps per
 	// scheduler a first-touch DRAM miss in the middle of the control law cannot be hidden otherwise.
 #ifndef OSC_NO_PREFETCH
@@ -135,7 +166,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	}
 #endif
 	KinDynS<N> kd;
-	forward_kinematics_s<N>(mdl, q, kd, smt, sms);
+	forward_kinematics_s<N, SPEC>(mdl, q, kd, smt, sms);
 
 	double tau[N];
 #pragma unroll
@@ -144,16 +175,21 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 
 	if constexpr (R == 0) {
 		// ---- a full JointTask alone: N_prec = I, range = I:  tau = M qdd_d + M_mod t   (JointTask.cpp:348-355)
-		if (P.gravity_comp)
-			mass_matrix_s<N, true>(mdl, kd, smt, sms);
+		if (!SPEC && P.gravity_comp)
+			mass_matrix_s<N, true, SPEC>(mdl, kd, smt, sms);
 		else
-			mass_matrix_s<N, false>(mdl, kd, smt, sms);
+			mass_matrix_s<N, false, SPEC>(mdl, kd, smt, sms);
 		const DevJt& t = P.jt[0];
 		const osc_joint_params& p = t.p;
 		double pid[N], acc[N];
 #pragma unroll
 		for (int j = 0; j < N; j++) pid[j] = acc[j] = 0.0;
-		if (alive) joint_control_law<N, N>(t, NR, i, q, dq, pid, acc);
+		if (alive) {
+			double dq[N];
+#pragma unroll
+			for (int j = 0; j < N; j++) dq[j] = P.dq[(int64_t)j * NR + i];
+			joint_control_law<N, N>(t, NR, i, q, dq, pid, acc);
+		}
 #pragma unroll
 		for (int r = 0; r < N; r++) {
 			double s = 0.0;
@@ -177,7 +213,29 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		double x[3], Rc[9];
 		frame_pose_s<N>(kd, t.body, t.ctrl_R, t.ctrl_t, x, Rc, smt, sms);
 
-		// ---- pass 1 over the Jacobian columns (never stored): G = J_t J_t^T and the task velocity J0 dq
+		// ---- dynamics first: M (composite rigid bodies), M = L L^T in place.  The body orientations in shared memory
+		// are dead after this, the factor takes their place; only diag(M) is kept for the bounded-inertia variant.
+		if (!SPEC && P.gravity_comp) {
+			mass_matrix_s<N, true, SPEC>(mdl, kd, smt, sms);
+#pragma unroll
+			for (int j = 0; j < N; j++) smt[(size_t)(kSmFactor<N> + N * R + j) * sms] = kd.g[j];
+		} else {
+			mass_matrix_s<N, false, SPEC>(mdl, kd, smt, sms);
+		}
+		double Mdiag[N];
+		SmTri<N, kCycleBlock> Ls{smt};
+		{
+			double invd[N];
+#pragma unroll
+			for (int j = 0; j < N; j++) Mdiag[j] = kd.M[j][j];
+			cholesky_lower<N>(kd.M, invd);
+			Ls.store(kd.M, invd);
+		}
+		OSC_LS();
+
+		// ---- one pass over the Jacobian columns: G = J_t J_t^T, the task velocity J0 dq, and the reduced columns
+		// staged in shared memory behind the factor (the joint axes and origins are dead after this loop)
+		double* Js = smt + (size_t)kSmFactor<N> * sms;
 		double v[3] = {0, 0, 0}, w[3] = {0, 0, 0};
 		{
 			double G[R][R];
@@ -188,27 +246,41 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 #pragma unroll
 			for (int j = 0; j < N; j++) {
 				double c6[6], cr[R];
-				jacobian_column<N>(mdl, kd, t.body, x, j, c6);
+				jacobian_column<N, SPEC>(mdl, kd, t.body, x, j, c6);
+				const double dqj = P.dq[(int64_t)j * NR + i];
 #pragma unroll
 				for (int k = 0; k < 3; k++) {
-					v[k] += c6[k] * dq[j];
-					w[k] += c6[3 + k] * dq[j];
+					v[k] += c6[k] * dqj;
+					w[k] += c6[3 + k] * dqj;
 				}
 				reduce_task_vector<R, FULL>(t, c6, cr);
+#pragma unroll
+				for (int a = 0; a < R; a++) Js[(j * R + a) * sms] = cr[a];
 #pragma unroll
 				for (int a = 0; a < R; a++)
 #pragma unroll
 					for (int b = 0; b <= a; b++) G[a][b] += cr[a] * cr[b];
-				OSC_LS();
 			}
+			OSC_LS();
 #pragma unroll
 			for (int a = 0; a < R; a++)
 #pragma unroll
 				for (int b = a + 1; b < R; b++) G[a][b] = G[b][a];
-			// Branch decision of SingularityHandler::updateTaskModel (:83-105), taken before any task state is touched and
-			// before the dynamics are evaluated: robots that are not provably non-singular are appended
-			// (warp-aggregated) to the list of the general-path kernel and leave this kernel.
-			const bool flagged = alive && !sound_nonsingular_gram<R>(G, p.s_max, p.s_abs_tol);
+			// Branch decision of SingularityHandler::updateTaskModel (:83-105), taken before any task state is touched:
+			// robots that are not provably non-singular are appended (warp-aggregated) to the list of the general-path
+			// kernel and leave this kernel.
+			bool leave = !sound_nonsingular_gram<R>(G, p.s_max, p.s_abs_tol);
+			if constexpr (SPEC) {
+				// the specialisation carries the rank-zero and rank-one bounded-inertia updates only
+				double hh[N], dd;
+				if (p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES && bie_shift<N>(Mdiag, p.bie_threshold, hh, dd) >= 2) leave = true;
+				if constexpr (HAS_JT) {
+					const osc_joint_params& jp0 = P.jt[0].p;
+					if (jp0.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES && bie_shift<N>(Mdiag, jp0.bie_threshold, hh, dd) >= 2)
+						leave = true;
+				}
+			}
+			const bool flagged = alive && leave;
 			const unsigned m = __ballot_sync(0xffffffffu, flagged);
 			if (flagged) {
 				const int lane = threadIdx.x & 31;
@@ -230,40 +302,25 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			t.ist[(int64_t)MI_HIST_SIZE * NR + i] = 0;
 		}
 
-		// ---- dynamics: M (composite rigid bodies), M = L L^T in place, factor staged in shared memory (the body
-		// orientations are dead from here on); only diag(M) is kept for the bounded-inertia variant
-		if (P.gravity_comp)
-			mass_matrix_s<N, true>(mdl, kd, smt, sms);
-		else
-			mass_matrix_s<N, false>(mdl, kd, smt, sms);
-		double Mdiag[N];
-		SmTri<N, kCycleBlock> Ls{smt};
-		{
-			double invd[N];
-#pragma unroll
-			for (int j = 0; j < N; j++) Mdiag[j] = kd.M[j][j];
-			cholesky_lower<N>(kd.M, invd);
-			Ls.store(kd.M, invd);
-		}
-
 		OSC_LS();
 		double yf[R], yF[R];
 		bool has_F;
 		{
 			double fstar[6] = {0, 0, 0, 0, 0, 0}, F[6] = {0, 0, 0, 0, 0, 0};
 			has_F = true;
-			if (alive) has_F = mft_control_law(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status);
+			if (alive) has_F = mft_control_law<SPEC>(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status);
 			reduce_task_vector<R, FULL>(t, fstar, yf);
 			reduce_task_vector<R, FULL>(t, F, yF);
 		}
+		OSC_LS();
 
-		// ---- pass 2 over the Jacobian columns: X = L^-1 J_t^T row by row (row r needs column r of J only)
+		// ---- X = L^-1 J_t^T row by row (row r needs column r of J only), operands from shared memory
 		double X[N][R];
 #pragma unroll
 		for (int r = 0; r < N; r++) {
-			double c6[6], cr[R];
-			jacobian_column<N>(mdl, kd, t.body, x, r, c6);
-			reduce_task_vector<R, FULL>(t, c6, cr);
+			double cr[R];
+#pragma unroll
+			for (int a = 0; a < R; a++) cr[a] = Js[(r * R + a) * sms];
 #pragma unroll
 			for (int k = 0; k < r; k++) {
 				const double l = Ls.L(r, k);
@@ -273,8 +330,8 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			const double inv = Ls.invd(r);
 #pragma unroll
 			for (int a = 0; a < R; a++) X[r][a] = cr[a] * inv;
-			OSC_LS();
 		}
+		OSC_LS();
 		// bounded inertia estimates: M_BIE = M + diag(d); with one clamped entry: M + delta e e^T,
 		// g = L^-1 e, mu = g.g, z = J M^-1 e = X^T g
 		const int dec = p.dynamic_decoupling_type;
@@ -322,7 +379,8 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			const double f = delta * zt / ((1.0 + delta * mu) - delta * zs);
 #pragma unroll
 			for (int a = 0; a < R; a++) yf[a] += sz[a] * f;
-		} else if (dec == OSC_BOUNDED_INERTIA_ESTIMATES) {
+		}
+		else if (!SPEC && dec == OSC_BOUNDED_INERTIA_ESTIMATES) {
 			// general route (two or more clamped entries): A_b = W^T W, W = L_b^-1 J_t^T with J_t^T = L Q [R; 0]
 			double Lf[N][N], Lb[N][N], invdb[N];
 #pragma unroll
@@ -395,7 +453,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 						qj[j] = P.q[(int64_t)j * NR + i];
 						dqj[j] = P.dq[(int64_t)j * NR + i];
 					}
-					joint_control_law<N, N>(jt, NR, i, qj, dqj, pid, acc);
+					joint_control_law<N, N, SPEC>(jt, NR, i, qj, dqj, pid, acc);
 				}
 		OSC_LS();
 				// Q_perp = H_1..H_R [0; I],  W = L^-T Q_perp,  K = L Q_perp
@@ -492,7 +550,8 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 						const double f = dj * cz / ((1.0 + dj * muj) - dj * cc);
 #pragma unroll
 						for (int a = 0; a < Mn; a++) z2[a] += c[a] * f;
-					} else if (kj >= 2) {
+					}
+					else if (!SPEC && kj >= 2) {
 						double Lf[N][N], Lb[N][N], invdb[N];
 #pragma unroll
 						for (int r = 0; r < N; r++)
@@ -534,6 +593,9 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		}
 	}
 
+#if defined(OSC_TRACE)
+	OSC_LS();
+#endif
 	// RobotController::computeControlTorques tail (RobotController.cpp:86-116)
 	if (P.torque_saturation) {
 #pragma unroll
@@ -544,9 +606,14 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				tau[j] = -mdl.effort[j];
 		}
 	}
-	if (P.gravity_comp) {
+	if (!SPEC && P.gravity_comp) {
 #pragma unroll
-		for (int j = 0; j < N; j++) tau[j] += kd.g[j];
+		for (int j = 0; j < N; j++) {
+			if constexpr (R == 0)
+				tau[j] += kd.g[j];
+			else
+				tau[j] += smt[(size_t)(kSmFactor<N> + N * R + j) * sms];
+		}
 	}
 	if (status & OSC_STATUS_UNHANDLED) {
 #pragma unroll

@@ -4,6 +4,13 @@
 #include "osc_singular.cuh"
 #include "osc_blend.cuh"
 #include "osc_launch.h"
+#include <algorithm>
+#include <cmath>
+#if defined(OSC_TRACE)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#endif
 
 #ifndef OSC_INST_N
 #error "compile with -DOSC_INST_N=<dof>"
@@ -16,19 +23,89 @@
 
 namespace osc {
 
-template <int N, int R, bool JT, bool FULL>
+// smallest eigenvalue of a symmetric 3 x 3 matrix (xx xy xz yy yz zz), trigonometric closed form
+static double min_eig_sym3(const double* I) {
+	const double a = I[0], b = I[3], c = I[5], d = I[1], e = I[2], f = I[4];
+	const double p1 = d * d + e * e + f * f;
+	const double q = (a + b + c) / 3.0;
+	if (p1 == 0.0) return std::min(a, std::min(b, c));
+	const double p2 = (a - q) * (a - q) + (b - q) * (b - q) + (c - q) * (c - q) + 2.0 * p1;
+	const double p = std::sqrt(p2 / 6.0);
+	const double B[6] = {(a - q) / p, d / p, e / p, (b - q) / p, f / p, (c - q) / p};
+	double r = 0.5 * (B[0] * (B[3] * B[5] - B[4] * B[4]) - B[1] * (B[1] * B[5] - B[4] * B[2]) + B[2] * (B[1] * B[4] - B[3] * B[2]));
+	r = std::max(-1.0, std::min(1.0, r));
+	const double phi = std::acos(r) / 3.0;
+	return q + 2.0 * p * std::cos(phi + 2.0 * 3.14159265358979323846 / 3.0);
+}
+
+// Conditions under which the specialised instantiation (SPEC, osc_cycle.cuh) computes the same thing as the general one.
+static bool cycle_spec_eligible(const OscProgram& P, bool has_jt) {
+	const DevModel& m = P.model;
+	for (int j = 0; j < m.n; j++)
+		if (m.jtype[j] != 0 || m.axis[j][0] != 0.0 || m.axis[j][1] != 0.0 || m.axis[j][2] != 1.0) return false;
+	if (P.gravity_comp) return false;
+	// The specialisation carries the bounded-inertia update of rank <= 1 only (robots needing more are handed to the
+	// general path one by one, which is correct but slow): require that at most one diagonal entry of M can ever fall
+	// below the threshold.  M_jj >= sum over the bodies the joint moves of their smallest principal moment of inertia.
+	{
+		double thr = 0.0;
+		if (P.mft[0].p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES) thr = std::max(thr, P.mft[0].p.bie_threshold);
+		if (has_jt && P.jt[0].p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES) thr = std::max(thr, P.jt[0].p.bie_threshold);
+		double lb = 0.0;
+		int may_clamp = 0;
+		for (int j = m.n - 1; j >= 0; j--) {
+			lb += min_eig_sym3(m.inertia[j]);
+			if (lb < thr) may_clamp++;
+		}
+		if (may_clamp > 1) return false;
+	}
+	const DevMft& t = P.mft[0];
+	const osc_mft_params& p = t.p;
+	if (!t.full || p.force_space_dimension != 0 || p.moment_space_dimension != 0 || p.closed_loop_force_control ||
+		p.closed_loop_moment_control || p.use_velocity_saturation || p.dynamic_decoupling_type == OSC_IMPEDANCE)
+		return false;
+	if (has_jt) {
+		const DevJt& j = P.jt[0];
+		if (!j.full || j.p.use_velocity_saturation || j.p.dynamic_decoupling_type == OSC_IMPEDANCE) return false;
+	}
+	return true;
+}
+
+template <int N, int R, bool JT, bool FULL, bool SPEC = false>
 static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 	const unsigned grid = (unsigned)((P.n_robots + kCycleBlock - 1) / kCycleBlock);
-	constexpr int smem = 9 * N * kCycleBlock * (int)sizeof(double);  // body orientations staged between the two passes
+	constexpr int smem = cycle_smem_doubles<N, R>() * kCycleBlock * (int)sizeof(double);
 	static bool configured[64] = {false};  // per device: function attributes belong to the device's context
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev < 0 || dev >= 64 || !configured[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(osc_cycle_kernel<N, R, JT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaError_t e = cudaFuncSetAttribute(osc_cycle_kernel<N, R, JT, FULL, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e != cudaSuccess) return e;
 		if (dev >= 0 && dev < 64) configured[dev] = true;
 	}
-	osc_cycle_kernel<N, R, JT, FULL><<<grid, kCycleBlock, smem, stream>>>(P);
+#if defined(OSC_TRACE)
+	static unsigned long long* d_trace = nullptr;
+	const size_t tbytes = (size_t)grid * 32 * 2 * sizeof(unsigned long long);
+	if (!d_trace) {
+		cudaMalloc(&d_trace, (size_t)1 << 26);
+		cudaMemcpyToSymbol(g_trace, &d_trace, sizeof(d_trace));
+	}
+	cudaMemsetAsync(d_trace, 0, tbytes, stream);
+#endif
+	osc_cycle_kernel<N, R, JT, FULL, SPEC><<<grid, kCycleBlock, smem, stream>>>(P);
+#if defined(OSC_TRACE)
+	if (const char* path = getenv("OSC_TRACE_FILE")) {
+		cudaStreamSynchronize(stream);
+		std::vector<unsigned long long> hbuf(tbytes / sizeof(unsigned long long));
+		cudaMemcpy(hbuf.data(), d_trace, tbytes, cudaMemcpyDeviceToHost);
+		if (FILE* f = fopen(path, "ab")) {
+			unsigned long long hdr[2] = {0x4f53435452414345ull, (unsigned long long)grid};
+			fwrite(hdr, sizeof(hdr), 1, f);
+			fwrite(hbuf.data(), 1, tbytes, f);
+			fclose(f);
+		}
+	}
+#endif
 	return cudaGetLastError();
 }
 
@@ -36,7 +113,10 @@ template <int N, int R, bool JT>
 static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 	cudaError_t e0;
 	if constexpr (R == 6) {
-		e0 = (P.mft[0].full) ? launch_variant<N, R, JT, true>(P, stream) : launch_variant<N, R, JT, false>(P, stream);
+		if (P.mft[0].full)
+			e0 = cycle_spec_eligible(P, JT) ? launch_variant<N, R, JT, true, true>(P, stream) : launch_variant<N, R, JT, true>(P, stream);
+		else
+			e0 = launch_variant<N, R, JT, false>(P, stream);
 	} else {
 		e0 = launch_variant<N, R, JT, false>(P, stream);
 	}

@@ -7,13 +7,41 @@
 // Phase barriers of the fused cycle kernel: the warps of a block walk the long, fully unrolled instruction stream
 // together, so an instruction-cache line fetched for one warp serves the others (measured +6 % on B200,
 // profiles/).  Legal because no thread of the block leaves the kernel early.
+#include "osc_dev_types.h"
+#include "osc_math.cuh"
+#if defined(OSC_TRACE)
+// Tuning builds only (tools/trace_phases.py): thread 0 of every block stamps the SM clock and the global timer at each
+// phase boundary into a buffer that the launcher dumps to $OSC_TRACE_FILE.
+namespace osc {
+__device__ unsigned long long* g_trace = nullptr;
+__shared__ int s_trace_k;
+DEVI void trace_point(bool sync) {
+	if (sync) __syncthreads();
+	if (threadIdx.x == 0 && g_trace) {
+		const int k = s_trace_k++;
+		unsigned long long g;
+		unsigned smid;
+		asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+		asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+		if (k < 31) {
+			g_trace[((size_t)blockIdx.x * 32 + k) * 2] = (unsigned long long)clock64();
+			g_trace[((size_t)blockIdx.x * 32 + k) * 2 + 1] = g;
+		}
+		g_trace[((size_t)blockIdx.x * 32 + 31) * 2] = smid;
+		g_trace[((size_t)blockIdx.x * 32 + 31) * 2 + 1] = k + 1;
+	}
+}
+}  // namespace osc
 #ifndef OSC_NO_PHASE_SYNC
+#define OSC_LS() osc::trace_point(true)
+#else
+#define OSC_LS() osc::trace_point(false)
+#endif
+#elif !defined(OSC_NO_PHASE_SYNC)
 #define OSC_LS() __syncthreads()
 #else
 #define OSC_LS() ((void)0)
 #endif
-#include "osc_dev_types.h"
-#include "osc_math.cuh"
 
 namespace osc {
 
@@ -239,10 +267,20 @@ struct KinDynS {
 	double g[N];
 };
 
-template <int N>
+// ZREV: every joint is revolute about its local z axis (checked on the host: model_all_revolute_z), so the per-joint
+// alternatives disappear from the instruction stream.
+template <int N, bool ZREV = false>
 DEVI void forward_kinematics_s(const DevModel& m, const double (&q)[N], KinDynS<N>& kd, double* smt, int sms) {
 	double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 	double p[3] = {0, 0, 0};
+	// all joint angles first: N independent polynomial chains instead of one per link of the serial chain below
+	double sn[N], cs[N];
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		sn[i] = 0.0;
+		cs[i] = 1.0;
+		if (ZREV || m.jtype[i] == 0) sincos_joint(q[i], &sn[i], &cs[i]);
+	}
 #pragma unroll
 	for (int i = 0; i < N; i++) {
 		double t[3];
@@ -252,10 +290,9 @@ DEVI void forward_kinematics_s(const DevModel& m, const double (&q)[N], KinDynS<
 		p[2] += t[2];
 		double Rn[9];
 		mat3_mul(R, m.R_fix[i], Rn);
-		const bool axis_z = (m.axis[i][0] == 0.0) && (m.axis[i][1] == 0.0) && (m.axis[i][2] == 1.0);
-		if (m.jtype[i] == 0) {
-			double s, c;
-			sincos(q[i], &s, &c);
+		const bool axis_z = ZREV || ((m.axis[i][0] == 0.0) && (m.axis[i][1] == 0.0) && (m.axis[i][2] == 1.0));
+		if (ZREV || m.jtype[i] == 0) {
+			const double s = sn[i], c = cs[i];
 			if (axis_z) {  // R = Rn Rz(q): only the first two columns mix
 #pragma unroll
 				for (int r = 0; r < 3; r++) {
@@ -290,7 +327,7 @@ DEVI void forward_kinematics_s(const DevModel& m, const double (&q)[N], KinDynS<
 	}
 }
 
-template <int N, bool WITH_GRAVITY>
+template <int N, bool WITH_GRAVITY, bool ZREV = false>
 DEVI void mass_matrix_s(const DevModel& m, KinDynS<N>& kd, const double* smt, int sms) {
 	double cm = 0.0, ch[3] = {0, 0, 0};
 	double cI[6] = {0, 0, 0, 0, 0, 0};	// xx xy xz yy yz zz
@@ -343,7 +380,7 @@ DEVI void mass_matrix_s(const DevModel& m, KinDynS<N>& kd, const double* smt, in
 		cI[5] += Iw[5] + mi * (cc - c[2] * c[2]);
 
 		double w[3], vo[3];
-		if (m.jtype[i] == 0) {
+		if (ZREV || m.jtype[i] == 0) {
 			w[0] = kd.a[i][0];
 			w[1] = kd.a[i][1];
 			w[2] = kd.a[i][2];
@@ -366,7 +403,7 @@ DEVI void mass_matrix_s(const DevModel& m, KinDynS<N>& kd, const double* smt, in
 #pragma unroll
 		for (int j = 0; j <= i; j++) {
 			// s_j . F_i = a_j . (n_o + f x p_j) for a revolute joint j,  a_j . f for a prismatic one
-			if (m.jtype[j] == 0) {
+			if (ZREV || m.jtype[j] == 0) {
 				double fxp[3];
 				cross3(f, kd.p[j], fxp);
 				kd.M[i][j] = kd.a[j][0] * (no[0] + fxp[0]) + kd.a[j][1] * (no[1] + fxp[1]) + kd.a[j][2] * (no[2] + fxp[2]);
@@ -413,10 +450,10 @@ DEVI void frame_pose_s(const KinDynS<N>& kd, int body, const double Rf[9], const
 }
 
 // column j of the 6 x n world-frame Jacobian (linear rows first) of point x fixed to body `body`
-template <int N>
+template <int N, bool ZREV = false>
 DEVI void jacobian_column(const DevModel& m, const KinDynS<N>& kd, int body, const double x[3], int j, double c6[6]) {
 	if (j <= body) {
-		if (m.jtype[j] == 0) {
+		if (ZREV || m.jtype[j] == 0) {
 			double d[3] = {x[0] - kd.p[j][0], x[1] - kd.p[j][1], x[2] - kd.p[j][2]};
 			double v[3];
 			cross3(kd.a[j], d, v);

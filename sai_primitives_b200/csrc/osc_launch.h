@@ -12,7 +12,11 @@ namespace osc {
 constexpr int kCycleBlock = OSC_CYCLE_BLOCK;
 
 // robot dofs the fused cycle kernel is instantiated for (one translation unit each, see Makefile)
+#ifdef OSC_TUNE_DOF7_ONLY  // tuning builds (tools/tune.sh): the Panda kernels only
+#define OSC_CYCLE_DOFS(X) X(7)
+#else
 #define OSC_CYCLE_DOFS(X) X(4) X(6) X(7) X(8)
+#endif
 
 // Fused control cycle for hierarchy signature (n, R, has_jt): R = rank of a leading MotionForceTask (0: none),
 // has_jt = a full JointTask closes the hierarchy; R < 0 selects the general-hierarchy kernel.

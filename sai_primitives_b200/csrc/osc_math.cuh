@@ -44,6 +44,76 @@ DEVI void mat3_mul_bt(const double A[9], const double B[9], double C[9]) {
 			C[3 * i + j] = A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1] + A[3 * i + 2] * B[3 * j + 2];
 }
 
+// ---- lean FP64 reciprocal / reciprocal square root / sine-cosine --------------------------------------------------
+// The CUDA library versions carry special-case branches (subnormals, infinities, huge arguments) that cost a
+// predicate test, a convergence barrier and a cold subroutine per call site: about 35 instructions for rsqrt(), 80 for
+// sincos(), inlined dozens of times in the fused kernel.  The arguments here are pivots of positive definite matrices,
+// squared column norms and joint angles, so the hardware seed (MUFU.RSQ64H / MUFU.RCP64H, about 20 bits) plus
+// straight-line Newton steps is enough: results are accurate to 1-2 ulp for normal positive arguments.
+DEVI double rsqrt_pos(double d) {
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+	double h = d * y;
+	double e = fma(-h, y, 1.0);	 // 1 - d y^2
+	y = fma(y * e, fma(e, 0.375, 0.5), y);	// third order: y (1 + e/2 + 3 e^2/8)
+	h = d * y;
+	e = fma(-h, y, 1.0);
+	return fma(y * e, 0.5, y);
+}
+DEVI double rcp_nz(double d) {
+	double y;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+	double e = fma(-d, y, 1.0);
+	y = fma(y, e, y);
+	e = fma(-d, y, 1.0);
+	y = fma(y, e, y);
+	e = fma(-d, y, 1.0);
+	return fma(y, e, y);
+}
+// sqrt of a positive normal number
+DEVI double sqrt_pos(double d) {
+	const double y = rsqrt_pos(d);
+	const double s = d * y;
+	return fma(fma(-s, s, d), 0.5 * y, s);
+}
+// a / b for finite a and normal b
+DEVI double div_nz(double a, double b) {
+	const double y = rcp_nz(b);
+	const double q = a * y;
+	return fma(fma(-b, q, a), y, q);
+}
+// sin and cos of a joint angle.  Cody-Waite reduction by pi/2 in two pieces (exact enough for |x| < 1e4: the error
+// of the reduced argument stays below 1e-19 |k|) and the minimax polynomials of fdlibm's __kernel_sin/__kernel_cos
+// on [-pi/4, pi/4]; larger arguments take the library routine.
+static __device__ __noinline__ void sincos_far(double x, double* sn, double* cs) { sincos(x, sn, cs); }
+DEVI void sincos_joint(double x, double* sn, double* cs) {
+	if (!(fabs(x) < 1.0e4)) {
+		sincos_far(x, sn, cs);
+		return;
+	}
+	const int q = __double2int_rn(x * 0.63661977236758134308);
+	const double k = (double)q;
+	double r = fma(-k, 1.57079632679489655800e+00, x);
+	r = fma(-k, 6.12323399573676603587e-17, r);
+	const double z = r * r;
+	double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+	ps = fma(z, ps, 2.75573137070700676789e-06);
+	ps = fma(z, ps, -1.98412698298579493134e-04);
+	ps = fma(z, ps, 8.33333333332248946124e-03);
+	ps = fma(z, ps, -1.66666666666666324348e-01);
+	const double s = fma(z * r, ps, r);
+	double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+	pc = fma(z, pc, -2.75573143513906633035e-07);
+	pc = fma(z, pc, 2.48015872894767294178e-05);
+	pc = fma(z, pc, -1.38888888888741095749e-03);
+	pc = fma(z, pc, 4.16666666666666019037e-02);
+	const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+	const double a = (q & 1) ? c : s;
+	const double b = (q & 1) ? s : c;
+	*sn = (q & 2) ? -a : a;
+	*cs = ((q + 1) & 2) ? -b : b;
+}
+
 // In-place Cholesky of the lower triangle of a symmetric positive definite matrix: A = L L^T.
 // invd[j] = 1 / L[j][j] is kept so that the triangular solves multiply instead of divide (one FP64 reciprocal
 // per pivot instead of one division per solve step).  Returns false when a pivot is not positive.
@@ -56,7 +126,7 @@ DEVI bool cholesky_lower(double (&A)[N][N], double (&invd)[N]) {
 #pragma unroll
 		for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
 		ok = ok && (d > 0.0);
-		const double inv = rsqrt(d);
+		const double inv = rsqrt_pos(d);
 		invd[j] = inv;
 		A[j][j] = d * inv;
 #pragma unroll
@@ -142,7 +212,7 @@ DEVI void householder_qr(double (&X)[N][R], double (&vhead)[R], double (&beta)[R
 		double nrm2 = 0.0;
 #pragma unroll
 		for (int i = k; i < N; i++) nrm2 += X[i][j] * X[i][j];
-		const double inrm = rsqrt(nrm2);
+		const double inrm = rsqrt_pos(nrm2);
 		const double nrm = nrm2 * inrm;
 		const double x0 = X[k][j];
 		const double alpha = (x0 >= 0.0) ? -nrm : nrm;
@@ -151,7 +221,7 @@ DEVI void householder_qr(double (&X)[N][R], double (&vhead)[R], double (&beta)[R
 		// v^T v = nrm2 - 2 alpha x0 + alpha^2 = 2 (nrm2 - alpha x0)
 		const double vv = 2.0 * (nrm2 - alpha * x0);
 		// beta = 2 / v^T v = 1 / (nrm (nrm + |x0|)):  one reciprocal, no division
-		const double b = (vv > 0.0) ? 2.0 * __drcp_rn(vv) : 0.0;
+		const double b = (vv > 0.0) ? 2.0 * rcp_nz(vv) : 0.0;
 		vhead[j] = v0;
 		beta[j] = b;
 #pragma unroll
@@ -243,7 +313,7 @@ DEVI bool sound_nonsingular(const double (&JT)[N][R], double thr, double abs_tol
 			for (int i = 0; i < R; i++) s += G2[a][i] * G2[i][b];
 			t8 += (a == b) ? s * s : 2.0 * s * s;
 		}
-	const double hi = sqrt(sqrt(sqrt(t8)));
+	const double hi = sqrt_pos(sqrt_pos(sqrt_pos(t8)));
 	const double shift = thr * thr * hi;
 #pragma unroll
 	for (int a = 0; a < R; a++) G[a][a] -= shift;
@@ -280,7 +350,7 @@ DEVI bool sound_nonsingular_gram(double (&G)[R][R], double thr, double abs_tol) 
 			for (int i = 0; i < R; i++) s += G2[a][i] * G2[i][b];
 			t8 += (a == b) ? s * s : 2.0 * s * s;
 		}
-	const double hi = sqrt(sqrt(sqrt(t8)));
+	const double hi = sqrt_pos(sqrt_pos(sqrt_pos(t8)));
 	const double shift = thr * thr * hi;
 #pragma unroll
 	for (int a = 0; a < R; a++) G[a][a] -= shift;

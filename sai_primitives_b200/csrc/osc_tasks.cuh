@@ -161,13 +161,16 @@ DEVI double pinv_gain(double k) { return (k > 1e-6) ? 1.0 / k : 0.0; }
 // x, R: pose of the compliant frame in the world; v_in, w_in: J0 dq of the full (unprojected) Jacobian.
 // Outputs the unit-mass force f* and the force-related terms F (world axes, 6 each); returns false when F is
 // identically zero (pure motion control of a full task), so that callers can skip it.
+// MOTION: the task is known (host check: mft_pure_motion) to be a full task under pure motion control without velocity
+// saturation, so only the two PID laws are compiled in.
+template <bool MOTION = false>
 DEVI bool mft_control_law(const DevMft& t, int64_t NR, int64_t i, const double x[3], const double R[9], const double v_in[3],
 						  const double w_in[3], bool write_observers, double fstar[6], double F[6], uint32_t& status) {
 	double* st = t.st;
 	const osc_mft_params& p = t.p;
 	const double dt = t.dt;
 	double v[3] = {v_in[0], v_in[1], v_in[2]}, w[3] = {w_in[0], w_in[1], w_in[2]};
-	if (!t.full) {	// _jacobian = P * J0  (MotionForceTask.cpp:280-282, 293-298)
+	if (!MOTION && !t.full) {	// _jacobian = P * J0  (MotionForceTask.cpp:280-282, 293-298)
 		double tv[3], tw[3];
 		mat3_vec(t.Pt, v, tv);
 		mat3_vec(t.Pr, w, tw);
@@ -191,8 +194,8 @@ DEVI bool mft_control_law(const DevMft& t, int64_t NR, int64_t i, const double x
 
 	// Pure motion control of a full task (no force/moment space, open loop): every sigma is 0 or the identity
 	// (MotionForceTask.cpp:892-971), the force-related terms vanish and only the two PID laws remain.
-	if (t.full && p.force_space_dimension == 0 && p.moment_space_dimension == 0 && !p.closed_loop_force_control &&
-		!p.closed_loop_moment_control) {
+	if (MOTION || (t.full && p.force_space_dimension == 0 && p.moment_space_dimension == 0 && !p.closed_loop_force_control &&
+				   !p.closed_loop_moment_control)) {
 		double Ip[3], Io[3];
 		load3(st, NR, i, MC_INT_POS, Ip);
 		load3(st, NR, i, MC_INT_ORI, Io);
@@ -201,14 +204,14 @@ DEVI bool mft_control_law(const DevMft& t, int64_t NR, int64_t i, const double x
 			const double ex = x[k] - xd[k];
 			Ip[k] += ex * dt;
 			Io[k] += ori_err_goal[k] * dt;
-			if (!p.use_velocity_saturation) {
+			if (MOTION || !p.use_velocity_saturation) {
 				fstar[k] = ad[k] - p.kp_pos[k] * ex - p.kv_pos[k] * (v[k] - vd[k]) - p.ki_pos[k] * Ip[k];
 				fstar[3 + k] = ald[k] - p.kp_ori[k] * ori_err_goal[k] - p.kv_ori[k] * (w[k] - wd[k]) - p.ki_ori[k] * Io[k];
 			}
 			F[k] = 0.0;
 			F[3 + k] = 0.0;
 		}
-		if (p.use_velocity_saturation) {
+		if (!MOTION && p.use_velocity_saturation) {
 			double vdes[3], wdes[3];
 #pragma unroll
 			for (int k = 0; k < 3; k++) {
@@ -239,6 +242,7 @@ DEVI bool mft_control_law(const DevMft& t, int64_t NR, int64_t i, const double x
 		return false;
 	}
 
+	if constexpr (MOTION) return false;
 	// selection matrices
 	const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 	double uf[3], um[3];
@@ -418,15 +422,25 @@ DEVI bool mft_control_law(const DevMft& t, int64_t NR, int64_t i, const double x
 
 // JointTask PID in task coordinates: returns t (pid "torques") and the desired acceleration.
 // e = S q - q_d etc.  (JointTask.cpp:299-346; Appendix C8: saturation loop uses the task dof)
-template <int N, int K>
+template <int N, int K, bool SPEC = false>  // SPEC: full selection, no velocity saturation (host check)
 DEVI void joint_control_law(const DevJt& t, int64_t NR, int64_t i, const double (&q)[N], const double (&dq)[N],
 							double (&pid)[K], double (&acc)[K]) {
 	double* st = t.st;
 	const osc_joint_params& p = t.p;
+	// all loads first, all stores last: the compiler cannot prove that the integrator stores do not alias the
+	// following goal loads, and would otherwise serialise one memory round trip per task coordinate
+	double gp[K], gv[K], I[K];
+#pragma unroll
+	for (int a = 0; a < K; a++) {
+		gp[a] = ST(JC_GOAL_POS, a);
+		gv[a] = ST(JC_GOAL_VEL, a);
+		acc[a] = ST(JC_GOAL_ACC, a);
+		I[a] = ST(JC_INT, a);
+	}
 #pragma unroll
 	for (int a = 0; a < K; a++) {
 		double pos, vel;
-		if (t.full) {
+		if (SPEC || t.full) {
 			pos = q[a];
 			vel = dq[a];
 		} else {
@@ -438,24 +452,22 @@ DEVI void joint_control_law(const DevJt& t, int64_t NR, int64_t i, const double 
 				vel += t.S[a][j] * dq[j];
 			}
 		}
-		const double e = pos - ST(JC_GOAL_POS, a);
-		const double vd = ST(JC_GOAL_VEL, a);
-		acc[a] = ST(JC_GOAL_ACC, a);
-		double I = ST(JC_INT, a);
-		I += e * t.dt;
-		ST(JC_INT, a) = I;
-		if (p.use_velocity_saturation) {
+		const double e = pos - gp[a];
+		I[a] += e * t.dt;
+		if (!SPEC && p.use_velocity_saturation) {
 			const double kvi = pinv_gain(p.kv[a]);
-			double vdes = -p.kp[a] * kvi * e - p.ki[a] * kvi * I;
+			double vdes = -p.kp[a] * kvi * e - p.ki[a] * kvi * I[a];
 			if (vdes > p.saturation_velocity[a])
 				vdes = p.saturation_velocity[a];
 			else if (vdes < -p.saturation_velocity[a])
 				vdes = -p.saturation_velocity[a];
 			pid[a] = -p.kv[a] * (vel - vdes);
 		} else {
-			pid[a] = -p.kp[a] * e - p.kv[a] * (vel - vd) - p.ki[a] * I;
+			pid[a] = -p.kp[a] * e - p.kv[a] * (vel - gv[a]) - p.ki[a] * I[a];
 		}
 	}
+#pragma unroll
+	for (int a = 0; a < K; a++) ST(JC_INT, a) = I[a];
 }
 
 // Same law with a run-time task dimension (general hierarchies, osc_singular.cuh)
