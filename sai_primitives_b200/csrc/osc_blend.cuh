@@ -745,6 +745,8 @@ DEVI bool blend_robot(const OscProgram& P, const int64_t i) {
 // Hand-over list of the fast kernel for the flagship hierarchy: unrolled blending path, general path as fallback.
 template <int N, bool HAS_JT>
 __global__ void __launch_bounds__(64) osc_blend_kernel(const __grid_constant__ OscProgram P) {
+	// let the next cycle's fast kernel get scheduled behind this one right away, then wait for the fast kernel of this cycle
+	asm volatile("griddepcontrol.launch_dependents;");
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 	const int32_t count = P.sing_count[P.sing_parity];
 	const int stride = gridDim.x * blockDim.x;

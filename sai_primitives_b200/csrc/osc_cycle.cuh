@@ -74,10 +74,21 @@ DEVI void bie_cholesky_from_factor(const double (&L)[N][N], const double (&d)[N]
 // reduced Jacobian columns and the gravity vector.
 template <int N>
 constexpr int kSmFactor = N * (N + 1) / 2 + N;
-template <int N, int R>
+template <int N, int R, bool SPEC = false>
 constexpr int cycle_smem_doubles() {
+	if (SPEC) return 15 * N;  // rolled kinematics layout (osc_kindyn.cuh); factor and Jacobian columns fit underneath
 	return (9 * N > kSmFactor<N> + N * R + N) ? 9 * N : kSmFactor<N> + N * R + N;
 }
+static_assert(kSmFactor<8> + 8 * 6 <= 15 * 8 && kSmFactor<8> <= 9 * 8, "rolled layout: the Jacobian columns must not run into live joint data");
+
+template <bool NARROW>
+struct IndexType {
+	using type = int64_t;
+};
+template <>
+struct IndexType<true> {
+	using type = uint32_t;
+};
 
 DEVI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -112,17 +123,24 @@ DEVI void reduce_task_vector(const DevMft& t, const double (&v6)[6], double (&y)
 template <int N, int R, bool HAS_JT, bool FULL, bool SPEC = false>
 __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(const __grid_constant__ OscProgram P) {
 	extern __shared__ double sm[];
+	// Programmatic dependent launch on both sides: the general-path kernel of this cycle may be scheduled into whatever
+	// the last wave leaves free (it waits for this grid to complete before it reads the hand-over list), and this kernel
+	// may itself have been scheduled while the general-path kernel of the previous cycle was still running: it waits for
+	// it below, after the prefetches.
+	asm volatile("griddepcontrol.launch_dependents;");
 #if defined(OSC_TRACE)
 	if (threadIdx.x == 0) s_trace_k = 0;
 	OSC_LS();
 #endif
-	const int64_t NR = P.n_robots;
-	const int64_t i_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i_raw == 0 && P.sing_count) P.sing_count[P.sing_parity ^ 1] = 0;
+	// element index type of the state blocks: 32 bits in the specialisation (the launcher checks the sizes)
+	using IDX = typename IndexType<SPEC>::type;
+	const IDX NR = (IDX)P.n_robots;
+	const IDX i_raw = (IDX)blockIdx.x * blockDim.x + threadIdx.x;
+
 	// Every thread of the block walks the whole kernel (the phase barriers below need all of them): threads past the
 	// end of the batch and robots handed to the general path keep computing on valid data but touch no state.
 	bool alive = i_raw < NR;
-	const int64_t i = alive ? i_raw : NR - 1;
+	const IDX i = alive ? i_raw : NR - 1;
 #if defined(OSC_MODEL_IN_SMEM)
 	// Model constants from shared memory (broadcast LDS into ordinary registers, freely hoisted by the scheduler)
 	// instead of the constant bank (LDCU into the few uniform registers, consumed in place).
@@ -140,33 +158,67 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	double* smt = sm + threadIdx.x;
 	constexpr int sms = kCycleBlock;  // the launcher always uses kCycleBlock threads per block
 
-	double q[N];
-#pragma unroll
-	for (int j = 0; j < N; j++) q[j] = P.q[(int64_t)j * NR + i];
-	// Warm L2/L1 with this robot's task state (goals, integrators) while the kinematics run: with two warps per
-	// scheduler a first-touch DRAM miss in the middle of the control law cannot be hidden otherwise.
+	// Warm L2 with this robot's inputs and task state (goals, integrators) before anything else: a first-touch DRAM miss
+	// in the middle of the control law cannot be hidden with two warps per scheduler, and a block that was scheduled
+	// while the previous kernel of the stream is still running (programmatic dependent launch) uses the wait for it.
+	// Prefetches are safe ahead of griddepcontrol.wait: they only move lines into L2, which stays coherent.
 #ifndef OSC_NO_PREFETCH
-	if constexpr (R > 0) {
-		const DevMft& t = P.mft[0];
-#pragma unroll
-		for (int c = 0; c < 24; c++) prefetch_l2(t.st + (int64_t)c * NR + i);
-#pragma unroll
-		for (int c = 0; c < 6; c++) prefetch_l2(t.st + (int64_t)(MC_INT_POS + c) * NR + i);
-		prefetch_l2(t.ist + (int64_t)MI_N_TYPES * NR + i);
-	}
-	if constexpr (HAS_JT || R == 0) {
-		const DevJt& jt = P.jt[0];
-#pragma unroll
-		for (int c = 0; c < N; c++) {
-			prefetch_l2(jt.st + (int64_t)(JC_GOAL_POS + c) * NR + i);
-			prefetch_l2(jt.st + (int64_t)(JC_GOAL_VEL + c) * NR + i);
-			prefetch_l2(jt.st + (int64_t)(JC_GOAL_ACC + c) * NR + i);
-			prefetch_l2(jt.st + (int64_t)(JC_INT + c) * NR + i);
+	{
+		// one bulk prefetch (cp.async.bulk.prefetch.L2) per state component and block: the block's robots are contiguous
+		// in every component row, so thread k asks for row k of the list below -- one instruction per thread instead of
+		// one prefetch per thread and component
+		const uint64_t b0 = (uint64_t)blockIdx.x * blockDim.x;
+		const uint64_t nrl = (uint64_t)P.n_robots;
+		const uint32_t cnt = (uint32_t)((nrl - b0 < (uint64_t)blockDim.x) ? (nrl - b0) : (uint64_t)blockDim.x);
+		int k = threadIdx.x;
+		const char* row = nullptr;
+		uint32_t esz = 8;
+		if (k < N) {
+			row = (const char*)(P.q + (uint64_t)k * nrl);
+		} else if ((k -= N) < N) {
+			row = (const char*)(P.dq + (uint64_t)k * nrl);
+		} else {
+			k -= N;
+			if constexpr (R > 0) {
+				const DevMft& t = P.mft[0];
+				if (k >= 0 && k < 24) row = (const char*)(t.st + (uint64_t)k * nrl);
+				else if (k >= 24 && k < 30) row = (const char*)(t.st + (uint64_t)(MC_INT_POS + k - 24) * nrl);
+				else if (k == 30) { row = (const char*)(t.ist + (uint64_t)MI_N_TYPES * nrl); esz = 4; }
+				k -= 31;
+			}
+			if constexpr (HAS_JT || R == 0) {
+				const DevJt& jt = P.jt[0];
+				if (k >= 0 && k < 4 * N) {
+					const int grp = k / N, c = k - grp * N;
+					const int comp = (grp == 0 ? JC_GOAL_POS : grp == 1 ? JC_GOAL_VEL : grp == 2 ? JC_GOAL_ACC : JC_INT) + c;
+					row = (const char*)(jt.st + (uint64_t)comp * nrl);
+				}
+			}
+		}
+		if (row) {
+			const uint64_t a0 = (uint64_t)(row + b0 * esz);
+			const uint64_t a = a0 & ~(uint64_t)15;
+			const uint32_t bytes = (uint32_t)((a0 - a) + (uint64_t)cnt * esz) & ~15u;  // stays inside the row's allocation
+			if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
 		}
 	}
 #endif
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	if (i_raw == 0 && P.sing_count) P.sing_count[P.sing_parity ^ 1] = 0;
+	double q[N];
+#pragma unroll
+	for (int j = 0; j < N; j++) q[j] = P.q[(IDX)j * NR + i];
 	KinDynS<N> kd;
-	forward_kinematics_s<N, SPEC>(mdl, q, kd, smt, sms);
+	if constexpr (SPEC) {
+#if defined(OSC_TRACE)
+		OSC_LS();
+#endif
+		forward_kinematics_rolled<N>(mdl, q, smt, sms);
+#if defined(OSC_TRACE)
+		OSC_LS();
+#endif
+	} else
+		forward_kinematics_s<N, false>(mdl, q, kd, smt, sms);
 
 	double tau[N];
 #pragma unroll
@@ -187,7 +239,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		if (alive) {
 			double dq[N];
 #pragma unroll
-			for (int j = 0; j < N; j++) dq[j] = P.dq[(int64_t)j * NR + i];
+			for (int j = 0; j < N; j++) dq[j] = P.dq[(IDX)j * NR + i];
 			joint_control_law<N, N>(t, NR, i, q, dq, pid, acc);
 		}
 #pragma unroll
@@ -211,16 +263,31 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		const DevMft& t = P.mft[0];
 		const osc_mft_params& p = t.p;
 		double x[3], Rc[9];
-		frame_pose_s<N>(kd, t.body, t.ctrl_R, t.ctrl_t, x, Rc, smt, sms);
+		if constexpr (SPEC)
+			frame_pose_rolled<N>(t.body, t.ctrl_R, t.ctrl_t, x, Rc, smt, sms);
+		else
+			frame_pose_s<N>(kd, t.body, t.ctrl_R, t.ctrl_t, x, Rc, smt, sms);
 
 		// ---- dynamics first: M (composite rigid bodies), M = L L^T in place.  The body orientations in shared memory
 		// are dead after this, the factor takes their place; only diag(M) is kept for the bounded-inertia variant.
-		if (!SPEC && P.gravity_comp) {
-			mass_matrix_s<N, true, SPEC>(mdl, kd, smt, sms);
+		double dqr[N];	// joint velocities for the Jacobian pass below, requested early
+		if constexpr (SPEC) {
+			mass_matrix_rolled<N>(mdl, smt, sms);
+#if defined(OSC_TRACE)
+			OSC_LS();
+#endif
+#pragma unroll
+			for (int j = 0; j < N; j++) dqr[j] = P.dq[(IDX)j * NR + i];
+#pragma unroll
+			for (int r = 0; r < N; r++)
+#pragma unroll
+				for (int c = 0; c <= r; c++) kd.M[r][c] = smt[(size_t)(9 * r + c) * sms];
+		} else if (P.gravity_comp) {
+			mass_matrix_s<N, true, false>(mdl, kd, smt, sms);
 #pragma unroll
 			for (int j = 0; j < N; j++) smt[(size_t)(kSmFactor<N> + N * R + j) * sms] = kd.g[j];
 		} else {
-			mass_matrix_s<N, false, SPEC>(mdl, kd, smt, sms);
+			mass_matrix_s<N, false, false>(mdl, kd, smt, sms);
 		}
 		double Mdiag[N];
 		SmTri<N, kCycleBlock> Ls{smt};
@@ -243,11 +310,46 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			for (int a = 0; a < R; a++)
 #pragma unroll
 				for (int b = 0; b < R; b++) G[a][b] = 0.0;
+			if constexpr (SPEC) {
+				// rolled: axis and origin of joint j from shared memory, dq_j by rotating the register file
+				static_assert(!SPEC || (R == 6 && FULL), "the specialisation is the full six-dof task");
+				const int nb = t.body + 1;	// joints beyond the task body do not move it
+#pragma unroll 1
+				for (int j = 0; j < N; j++) {
+					const double* ap = smt + (size_t)(kSmAxes<N> + 6 * j) * sms;
+					const double a3[3] = {ap[0], ap[1 * sms], ap[2 * sms]};
+					const double d[3] = {x[0] - ap[3 * sms], x[1] - ap[4 * sms], x[2] - ap[5 * sms]};
+					const double mk = (j < nb) ? 1.0 : 0.0;
+					const double dqj = dqr[0];
 #pragma unroll
-			for (int j = 0; j < N; j++) {
+					for (int k = 0; k + 1 < N; k++) dqr[k] = dqr[k + 1];
+					double cr[6];
+					cross3(a3, d, cr);
+					cr[0] *= mk;
+					cr[1] *= mk;
+					cr[2] *= mk;
+					cr[3] = a3[0] * mk;
+					cr[4] = a3[1] * mk;
+					cr[5] = a3[2] * mk;
+#pragma unroll
+					for (int k = 0; k < 3; k++) {
+						v[k] += cr[k] * dqj;
+						w[k] += cr[3 + k] * dqj;
+					}
+					double* Jj = Js + (size_t)(j * R) * sms;
+#pragma unroll
+					for (int a = 0; a < R; a++) Jj[a * sms] = cr[a];
+#pragma unroll
+					for (int a = 0; a < R; a++)
+#pragma unroll
+						for (int b = 0; b <= a; b++) G[a][b] += cr[a] * cr[b];
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < (SPEC ? 0 : N); j++) {
 				double c6[6], cr[R];
-				jacobian_column<N, SPEC>(mdl, kd, t.body, x, j, c6);
-				const double dqj = P.dq[(int64_t)j * NR + i];
+				jacobian_column<N, false>(mdl, kd, t.body, x, j, c6);
+				const double dqj = P.dq[(IDX)j * NR + i];
 #pragma unroll
 				for (int k = 0; k < 3; k++) {
 					v[k] += c6[k] * dqj;
@@ -294,12 +396,12 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		}
 		// classifySingularity with an empty singular range clears the handler memory (:239-245); only robots that
 		// were singular at the previous update have anything to clear
-		if (alive && P.update_models && t.ist[(int64_t)MI_N_TYPES * NR + i] != 0) {
-			t.ist[(int64_t)MI_N_TYPES * NR + i] = 0;
-			t.ist[(int64_t)MI_T1_COUNTER * NR + i] = 0;
-			t.ist[(int64_t)MI_T2_COUNTER * NR + i] = 0;
-			t.ist[(int64_t)MI_HIST_HEAD * NR + i] = 0;
-			t.ist[(int64_t)MI_HIST_SIZE * NR + i] = 0;
+		if (alive && P.update_models && t.ist[(IDX)MI_N_TYPES * NR + i] != 0) {
+			t.ist[(IDX)MI_N_TYPES * NR + i] = 0;
+			t.ist[(IDX)MI_T1_COUNTER * NR + i] = 0;
+			t.ist[(IDX)MI_T2_COUNTER * NR + i] = 0;
+			t.ist[(IDX)MI_HIST_HEAD * NR + i] = 0;
+			t.ist[(IDX)MI_HIST_SIZE * NR + i] = 0;
 		}
 
 		OSC_LS();
@@ -450,8 +552,8 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 					double qj[N], dqj[N];  // re-read (L2 hot) rather than kept live across the task above
 #pragma unroll
 					for (int j = 0; j < N; j++) {
-						qj[j] = P.q[(int64_t)j * NR + i];
-						dqj[j] = P.dq[(int64_t)j * NR + i];
+						qj[j] = P.q[(IDX)j * NR + i];
+						dqj[j] = P.dq[(IDX)j * NR + i];
 					}
 					joint_control_law<N, N, SPEC>(jt, NR, i, qj, dqj, pid, acc);
 				}
@@ -621,7 +723,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	}
 	if (alive) {
 #pragma unroll
-		for (int j = 0; j < N; j++) P.tau[(int64_t)j * NR + i] = tau[j];
+		for (int j = 0; j < N; j++) P.tau[(IDX)j * NR + i] = tau[j];
 		P.status[i] = status;
 	}
 }

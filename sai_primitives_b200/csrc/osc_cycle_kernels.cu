@@ -43,7 +43,8 @@ static bool cycle_spec_eligible(const OscProgram& P, bool has_jt) {
 	const DevModel& m = P.model;
 	for (int j = 0; j < m.n; j++)
 		if (m.jtype[j] != 0 || m.axis[j][0] != 0.0 || m.axis[j][1] != 0.0 || m.axis[j][2] != 1.0) return false;
-	if (P.gravity_comp) return false;
+	if (P.gravity_comp || P.mft[0].body < 0) return false;
+	if ((unsigned long long)P.n_robots * (unsigned long long)MC_COUNT >= (1ull << 32)) return false;  // 32-bit element indices
 	// The specialisation carries the bounded-inertia update of rank <= 1 only (robots needing more are handed to the
 	// general path one by one, which is correct but slow): require that at most one diagonal entry of M can ever fall
 	// below the threshold.  M_jj >= sum over the bodies the joint moves of their smallest principal moment of inertia.
@@ -74,7 +75,7 @@ static bool cycle_spec_eligible(const OscProgram& P, bool has_jt) {
 template <int N, int R, bool JT, bool FULL, bool SPEC = false>
 static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 	const unsigned grid = (unsigned)((P.n_robots + kCycleBlock - 1) / kCycleBlock);
-	constexpr int smem = cycle_smem_doubles<N, R>() * kCycleBlock * (int)sizeof(double);
+	constexpr int smem = cycle_smem_doubles<N, R, SPEC>() * kCycleBlock * (int)sizeof(double);
 	static bool configured[64] = {false};  // per device: function attributes belong to the device's context
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -92,7 +93,20 @@ static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 	}
 	cudaMemsetAsync(d_trace, 0, tbytes, stream);
 #endif
-	osc_cycle_kernel<N, R, JT, FULL, SPEC><<<grid, kCycleBlock, smem, stream>>>(P);
+	{
+		cudaLaunchConfig_t cfg{};
+		cfg.gridDim = dim3(grid);
+		cfg.blockDim = dim3(kCycleBlock);
+		cfg.dynamicSmemBytes = smem;
+		cfg.stream = stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr;
+		cfg.numAttrs = 1;
+		cudaError_t e = cudaLaunchKernelEx(&cfg, osc_cycle_kernel<N, R, JT, FULL, SPEC>, P);
+		if (e != cudaSuccess) return e;
+	}
 #if defined(OSC_TRACE)
 	if (const char* path = getenv("OSC_TRACE_FILE")) {
 		cudaStreamSynchronize(stream);

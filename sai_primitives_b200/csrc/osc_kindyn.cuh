@@ -420,6 +420,150 @@ DEVI void mass_matrix_s(const DevModel& m, KinDynS<N>& kd, const double* smt, in
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Rolled kinematics / dynamics for chains whose joints are all revolute about their local z axis (the SPEC
+// instantiation of the fused kernel).  The loops over the joints are real loops: the per-joint quantities live in
+// shared memory under a run-time index and the model constants come from the constant bank under a uniform index,
+// so this stage costs about 500 instructions of code instead of 2,400 (the instruction stream of the whole kernel
+// has to stay inside the instruction cache, profiles/r01_ifetch.md).  Shared-memory slots of a thread, in doubles:
+//   [0, 9 N)      body orientations R_j, row major; row i of the mass matrix later takes the place of R_i
+//   [9 N, 15 N)   joint axis a_j (3) and joint origin p_j (3), world
+template <int N>
+constexpr int kSmAxes = 9 * N;
+
+// forward kinematics; qr[] holds the joint angles and is consumed (rotated) so that no run-time register index appears
+template <int N>
+DEVI void forward_kinematics_rolled(const DevModel& m, double (&qr)[N], double* smt, int sms) {
+	double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+	double p[3] = {0, 0, 0};
+#pragma unroll 1
+	for (int i = 0; i < N; i++) {
+		double s, c;
+		sincos_joint(qr[0], &s, &c);
+#pragma unroll
+		for (int k = 0; k + 1 < N; k++) qr[k] = qr[k + 1];
+		double t[3];
+		mat3_vec(R, m.t_fix[i], t);
+		p[0] += t[0];
+		p[1] += t[1];
+		p[2] += t[2];
+		double Rn[9];
+		mat3_mul(R, m.R_fix[i], Rn);
+#pragma unroll
+		for (int r = 0; r < 3; r++) {  // R = Rn Rz(q): only the first two columns mix
+			const double c0 = Rn[3 * r], c1 = Rn[3 * r + 1];
+			R[3 * r] = c * c0 + s * c1;
+			R[3 * r + 1] = c * c1 - s * c0;
+			R[3 * r + 2] = Rn[3 * r + 2];
+		}
+		double* Rs = smt + (size_t)(9 * i) * sms;
+#pragma unroll
+		for (int k = 0; k < 9; k++) Rs[k * sms] = R[k];
+		double* ap = smt + (size_t)(kSmAxes<N> + 6 * i) * sms;
+		ap[0] = R[2];
+		ap[1 * sms] = R[5];
+		ap[2 * sms] = R[8];
+		ap[3 * sms] = p[0];
+		ap[4 * sms] = p[1];
+		ap[5 * sms] = p[2];
+	}
+}
+
+// composite-rigid-body mass matrix; on exit M(i, j), j <= i, is at slot 9 i + j
+template <int N>
+DEVI void mass_matrix_rolled(const DevModel& m, double* smt, int sms) {
+	double a[N][3], p[N][3];
+#pragma unroll
+	for (int j = 0; j < N; j++)
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			a[j][k] = smt[(size_t)(kSmAxes<N> + 6 * j + k) * sms];
+			p[j][k] = smt[(size_t)(kSmAxes<N> + 6 * j + 3 + k) * sms];
+		}
+	double cm = 0.0, ch[3] = {0, 0, 0};
+	double cI[6] = {0, 0, 0, 0, 0, 0};	// xx xy xz yy yz zz
+#pragma unroll 1
+	for (int i = N - 1; i >= 0; i--) {
+		double* Rs = smt + (size_t)(9 * i) * sms;
+		double R[9];
+#pragma unroll
+		for (int k = 0; k < 9; k++) R[k] = Rs[k * sms];
+		const double* ap = smt + (size_t)(kSmAxes<N> + 6 * i) * sms;
+		const double ai[3] = {ap[0], ap[1 * sms], ap[2 * sms]};
+		const double pi[3] = {ap[3 * sms], ap[4 * sms], ap[5 * sms]};
+		const double* Ib = m.inertia[i];
+		double T[9];  // T = R * I
+#pragma unroll
+		for (int r = 0; r < 3; r++) {
+			T[3 * r + 0] = R[3 * r] * Ib[0] + R[3 * r + 1] * Ib[1] + R[3 * r + 2] * Ib[2];
+			T[3 * r + 1] = R[3 * r] * Ib[1] + R[3 * r + 1] * Ib[3] + R[3 * r + 2] * Ib[4];
+			T[3 * r + 2] = R[3 * r] * Ib[2] + R[3 * r + 1] * Ib[4] + R[3 * r + 2] * Ib[5];
+		}
+		double Iw[6];
+		Iw[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2];
+		Iw[1] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5];
+		Iw[2] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8];
+		Iw[3] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5];
+		Iw[4] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8];
+		Iw[5] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8];
+		double c[3];
+		mat3_vec(R, m.com[i], c);
+		c[0] += pi[0];
+		c[1] += pi[1];
+		c[2] += pi[2];
+		const double mi = m.mass[i];
+		const double cc = dot3(c, c);
+		cm += mi;
+		ch[0] += mi * c[0];
+		ch[1] += mi * c[1];
+		ch[2] += mi * c[2];
+		cI[0] += Iw[0] + mi * (cc - c[0] * c[0]);
+		cI[1] += Iw[1] - mi * c[0] * c[1];
+		cI[2] += Iw[2] - mi * c[0] * c[2];
+		cI[3] += Iw[3] + mi * (cc - c[1] * c[1]);
+		cI[4] += Iw[4] - mi * c[1] * c[2];
+		cI[5] += Iw[5] + mi * (cc - c[2] * c[2]);
+		// spatial momentum of the composite under a unit velocity of joint i (w = a_i, v_o = p_i x a_i)
+		double vo[3], f[3], no[3], t1[3];
+		cross3(pi, ai, vo);
+		cross3(ai, ch, t1);
+		f[0] = cm * vo[0] + t1[0];
+		f[1] = cm * vo[1] + t1[1];
+		f[2] = cm * vo[2] + t1[2];
+		cross3(ch, vo, t1);
+		no[0] = cI[0] * ai[0] + cI[1] * ai[1] + cI[2] * ai[2] + t1[0];
+		no[1] = cI[1] * ai[0] + cI[3] * ai[1] + cI[4] * ai[2] + t1[1];
+		no[2] = cI[2] * ai[0] + cI[4] * ai[1] + cI[5] * ai[2] + t1[2];
+		// M(i, j) = a_j . (n_o + f x p_j); evaluated for every j (the entries above the diagonal are never read) so that
+		// the register indices stay compile-time constants
+#pragma unroll
+		for (int j = 0; j < N; j++) {
+			double fxp[3];
+			cross3(f, p[j], fxp);
+			Rs[j * sms] = a[j][0] * (no[0] + fxp[0]) + a[j][1] * (no[1] + fxp[1]) + a[j][2] * (no[2] + fxp[2]);
+		}
+	}
+}
+
+// pose of a frame (Rf, tf given in the body frame) in the world from the rolled layout; body >= 0
+template <int N>
+DEVI void frame_pose_rolled(int body, const double Rf[9], const double tf[3], double x[3], double R[9], const double* smt, int sms) {
+	double Rb[9], pb[3];
+	const double* Rs = smt + (size_t)(9 * body) * sms;
+#pragma unroll
+	for (int k = 0; k < 9; k++) Rb[k] = Rs[k * sms];
+	const double* ap = smt + (size_t)(kSmAxes<N> + 6 * body) * sms;
+	pb[0] = ap[3 * sms];
+	pb[1] = ap[4 * sms];
+	pb[2] = ap[5 * sms];
+	double t[3];
+	mat3_vec(Rb, tf, t);
+	x[0] = pb[0] + t[0];
+	x[1] = pb[1] + t[1];
+	x[2] = pb[2] + t[2];
+	mat3_mul(Rb, Rf, R);
+}
+
 // pose of a frame (Rf, tf given in the body frame) in the world; body orientation read back from shared memory
 template <int N>
 DEVI void frame_pose_s(const KinDynS<N>& kd, int body, const double Rf[9], const double tf[3], double x[3], double R[9],

@@ -577,6 +577,7 @@ static __device__ __noinline__ void generic_cycle_one(const OscProgram& P, const
 template <int N>
 __global__ void __launch_bounds__(64, OSC_GENERIC_MIN_BLOCKS) osc_singular_kernel(const __grid_constant__ OscProgram P) {
 	// programmatic dependent launch: wait until the fast kernel of this cycle has completed and flushed its writes
+	asm volatile("griddepcontrol.launch_dependents;");
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 	const int32_t count = P.sing_count[P.sing_parity];
 	const int stride = gridDim.x * blockDim.x;

@@ -11,14 +11,18 @@
 
 namespace osc {
 
-#define ST(comp, c) st[(int64_t)((comp) + (c)) * NR + i]
+// IDX is int64_t in general; the SPEC instantiation of the fused kernel uses uint32_t (host check: every state block has
+// fewer than 2^32 elements), which halves the integer work per access.
+#define ST(comp, c) st[(decltype(NR))((comp) + (c)) * NR + i]
 
-DEVI void load3(const double* st, int64_t NR, int64_t i, int comp, double v[3]) {
+template <typename IDX>
+DEVI void load3(const double* st, IDX NR, IDX i, int comp, double v[3]) {
 	v[0] = ST(comp, 0);
 	v[1] = ST(comp, 1);
 	v[2] = ST(comp, 2);
 }
-DEVI void store3(double* st, int64_t NR, int64_t i, int comp, const double v[3]) {
+template <typename IDX>
+DEVI void store3(double* st, IDX NR, IDX i, int comp, const double v[3]) {
 	ST(comp, 0) = v[0];
 	ST(comp, 1) = v[1];
 	ST(comp, 2) = v[2];
@@ -76,7 +80,8 @@ DEVI void sigma_complement(const double P[9], const double S[9], double C[9]) {
 }
 
 // POPC step on the state of robot i.  fd, fs, vcl, vr are already sigma_force-projected.
-DEVI void popc_step(const DevMft& t, int64_t NR, int64_t i, const double fd[3], const double fs[3], const double vcl[3],
+template <typename IDX>
+DEVI void popc_step(const DevMft& t, IDX NR, IDX i, const double fd[3], const double fs[3], const double vcl[3],
 					const double vr[3], double kv, double kff, double out[3], uint32_t& status) {
 	double* st = t.st;
 	int32_t* ist = t.ist;
@@ -163,8 +168,8 @@ DEVI double pinv_gain(double k) { return (k > 1e-6) ? 1.0 / k : 0.0; }
 // identically zero (pure motion control of a full task), so that callers can skip it.
 // MOTION: the task is known (host check: mft_pure_motion) to be a full task under pure motion control without velocity
 // saturation, so only the two PID laws are compiled in.
-template <bool MOTION = false>
-DEVI bool mft_control_law(const DevMft& t, int64_t NR, int64_t i, const double x[3], const double R[9], const double v_in[3],
+template <bool MOTION = false, typename IDX = int64_t>
+DEVI bool mft_control_law(const DevMft& t, IDX NR, IDX i, const double x[3], const double R[9], const double v_in[3],
 						  const double w_in[3], bool write_observers, double fstar[6], double F[6], uint32_t& status) {
 	double* st = t.st;
 	const osc_mft_params& p = t.p;
@@ -422,8 +427,8 @@ DEVI bool mft_control_law(const DevMft& t, int64_t NR, int64_t i, const double x
 
 // JointTask PID in task coordinates: returns t (pid "torques") and the desired acceleration.
 // e = S q - q_d etc.  (JointTask.cpp:299-346; Appendix C8: saturation loop uses the task dof)
-template <int N, int K, bool SPEC = false>  // SPEC: full selection, no velocity saturation (host check)
-DEVI void joint_control_law(const DevJt& t, int64_t NR, int64_t i, const double (&q)[N], const double (&dq)[N],
+template <int N, int K, bool SPEC = false, typename IDX = int64_t>  // SPEC: full selection, no velocity saturation (host check)
+DEVI void joint_control_law(const DevJt& t, IDX NR, IDX i, const double (&q)[N], const double (&dq)[N],
 							double (&pid)[K], double (&acc)[K]) {
 	double* st = t.st;
 	const osc_joint_params& p = t.p;
