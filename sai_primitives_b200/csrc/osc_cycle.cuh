@@ -76,7 +76,9 @@ template <int N>
 constexpr int kSmFactor = N * (N + 1) / 2 + N;
 template <int N, int R, bool SPEC = false>
 constexpr int cycle_smem_doubles() {
-	if (SPEC) return 15 * N;  // rolled kinematics layout (osc_kindyn.cuh); factor and Jacobian columns fit underneath
+	// rolled kinematics layout (osc_kindyn.cuh); factor and Jacobian columns fit underneath, the staged goals of the
+	// motion-force task (30) go behind the Jacobian columns, those of the joint task (6 N) later take their place
+	if (SPEC) return (15 * N > kSmFactor<N> + N * R + 30) ? 15 * N : kSmFactor<N> + N * R + 30;
 	return (9 * N > kSmFactor<N> + N * R + N) ? 9 * N : kSmFactor<N> + N * R + N;
 }
 static_assert(kSmFactor<8> + 8 * 6 <= 15 * 8 && kSmFactor<8> <= 9 * 8, "rolled layout: the Jacobian columns must not run into live joint data");
@@ -89,6 +91,17 @@ template <>
 struct IndexType<true> {
 	using type = uint32_t;
 };
+
+// phase barrier of the kernel body: the specialisation (instruction stream inside the cache, no spills to fence) runs
+// without them
+#if defined(OSC_TRACE)
+#define OSC_LS_K() OSC_LS()
+#else
+#define OSC_LS_K()      \
+	do {                 \
+		if constexpr (!SPEC) OSC_LS(); \
+	} while (0)
+#endif
 
 DEVI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -130,7 +143,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	asm volatile("griddepcontrol.launch_dependents;");
 #if defined(OSC_TRACE)
 	if (threadIdx.x == 0) s_trace_k = 0;
-	OSC_LS();
+	OSC_LS_K();
 #endif
 	// element index type of the state blocks: 32 bits in the specialisation (the launcher checks the sizes)
 	using IDX = typename IndexType<SPEC>::type;
@@ -167,8 +180,8 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		// one bulk prefetch (cp.async.bulk.prefetch.L2) per state component and block: the block's robots are contiguous
 		// in every component row, so thread k asks for row k of the list below -- one instruction per thread instead of
 		// one prefetch per thread and component
-		const uint64_t b0 = (uint64_t)blockIdx.x * blockDim.x;
 		const uint64_t nrl = (uint64_t)P.n_robots;
+		const uint64_t b0 = (uint64_t)blockIdx.x * blockDim.x;
 		const uint32_t cnt = (uint32_t)((nrl - b0 < (uint64_t)blockDim.x) ? (nrl - b0) : (uint64_t)blockDim.x);
 		int k = threadIdx.x;
 		const char* row = nullptr;
@@ -211,11 +224,11 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	KinDynS<N> kd;
 	if constexpr (SPEC) {
 #if defined(OSC_TRACE)
-		OSC_LS();
+		OSC_LS_K();
 #endif
 		forward_kinematics_rolled<N>(mdl, q, smt, sms);
 #if defined(OSC_TRACE)
-		OSC_LS();
+		OSC_LS_K();
 #endif
 	} else
 		forward_kinematics_s<N, false>(mdl, q, kd, smt, sms);
@@ -274,7 +287,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		if constexpr (SPEC) {
 			mass_matrix_rolled<N>(mdl, smt, sms);
 #if defined(OSC_TRACE)
-			OSC_LS();
+			OSC_LS_K();
 #endif
 #pragma unroll
 			for (int j = 0; j < N; j++) dqr[j] = P.dq[(IDX)j * NR + i];
@@ -298,7 +311,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			cholesky_lower<N>(kd.M, invd);
 			Ls.store(kd.M, invd);
 		}
-		OSC_LS();
+		OSC_LS_K();
 
 		// ---- one pass over the Jacobian columns: G = J_t J_t^T, the task velocity J0 dq, and the reduced columns
 		// staged in shared memory behind the factor (the joint axes and origins are dead after this loop)
@@ -311,7 +324,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 #pragma unroll
 				for (int b = 0; b < R; b++) G[a][b] = 0.0;
 			if constexpr (SPEC) {
-				// rolled: axis and origin of joint j from shared memory, dq_j by rotating the register file
+				// rolled: axis, origin and velocity of joint j from shared memory
 				static_assert(!SPEC || (R == 6 && FULL), "the specialisation is the full six-dof task");
 				const int nb = t.body + 1;	// joints beyond the task body do not move it
 #pragma unroll 1
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 					const double a3[3] = {ap[0], ap[1 * sms], ap[2 * sms]};
 					const double d[3] = {x[0] - ap[3 * sms], x[1] - ap[4 * sms], x[2] - ap[5 * sms]};
 					const double mk = (j < nb) ? 1.0 : 0.0;
-					const double dqj = dqr[0];
+					const double dqj = dqr[0];	// rotate the register file: no run-time register index
 #pragma unroll
 					for (int k = 0; k + 1 < N; k++) dqr[k] = dqr[k + 1];
 					double cr[6];
@@ -345,6 +358,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 						for (int b = 0; b <= a; b++) G[a][b] += cr[a] * cr[b];
 				}
 			}
+			if constexpr (SPEC) mft_stage_goals(t, NR, i, smt + (size_t)(kSmFactor<N> + N * R) * sms, sms);
 #pragma unroll
 			for (int j = 0; j < (SPEC ? 0 : N); j++) {
 				double c6[6], cr[R];
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 #pragma unroll
 					for (int b = 0; b <= a; b++) G[a][b] += cr[a] * cr[b];
 			}
-			OSC_LS();
+			OSC_LS_K();
 #pragma unroll
 			for (int a = 0; a < R; a++)
 #pragma unroll
@@ -404,17 +418,19 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			t.ist[(IDX)MI_HIST_SIZE * NR + i] = 0;
 		}
 
-		OSC_LS();
+		OSC_LS_K();
 		double yf[R], yF[R];
 		bool has_F;
 		{
 			double fstar[6] = {0, 0, 0, 0, 0, 0}, F[6] = {0, 0, 0, 0, 0, 0};
 			has_F = true;
-			if (alive) has_F = mft_control_law<SPEC>(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status);
+			if (alive)
+				has_F = mft_control_law<SPEC>(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status,
+											  SPEC ? smt + (size_t)(kSmFactor<N> + N * R) * sms : nullptr, sms);
 			reduce_task_vector<R, FULL>(t, fstar, yf);
 			reduce_task_vector<R, FULL>(t, F, yF);
 		}
-		OSC_LS();
+		OSC_LS_K();
 
 		// ---- X = L^-1 J_t^T row by row (row r needs column r of J only), operands from shared memory
 		double X[N][R];
@@ -433,7 +449,10 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 #pragma unroll
 			for (int a = 0; a < R; a++) X[r][a] = cr[a] * inv;
 		}
-		OSC_LS();
+		// the Jacobian columns are dead: their slots receive the joint task's goals, integrator and q, dq, requested now
+		// and read after the factorisation below
+		if constexpr (SPEC && HAS_JT) joint_stage_goals<N>(P.jt[0], P.q, P.dq, NR, i, smt + (size_t)kSmFactor<N> * sms, sms);
+		OSC_LS_K();
 		// bounded inertia estimates: M_BIE = M + diag(d); with one clamped entry: M + delta e e^T,
 		// g = L^-1 e, mu = g.g, z = J M^-1 e = X^T g
 		const int dec = p.dynamic_decoupling_type;
@@ -458,10 +477,10 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				}
 			}
 		}
-		OSC_LS();
+		OSC_LS_K();
 		double vhead[R], beta[R], rinv[R];
 		householder_qr<N, R, 0>(X, vhead, beta, rinv);
-		OSC_LS();
+		OSC_LS_K();
 
 		if (dec == OSC_FULL_DYNAMIC_DECOUPLING || (dec == OSC_BOUNDED_INERTIA_ESTIMATES && kclamp == 0)) {
 			solve_rtr<N, R, 0>(X, rinv, yf);
@@ -515,7 +534,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			cholesky_lower<R>(Ab, invda);
 			solve_spd<R>(Ab, invda, yf);
 		}  // IMPEDANCE: Lambda_modified = I
-		OSC_LS();
+		OSC_LS_K();
 		// tau_task = J_t^T y = L Q [R y; 0]
 		{
 			if (has_F) {
@@ -548,7 +567,9 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				double pid[N], acc[N];
 #pragma unroll
 				for (int j = 0; j < N; j++) pid[j] = acc[j] = 0.0;
-				if (alive) {
+				if constexpr (SPEC) {
+					if (alive) joint_control_law_staged<N>(jt, NR, i, smt + (size_t)kSmFactor<N> * sms, sms, pid, acc);
+				} else if (alive) {
 					double qj[N], dqj[N];  // re-read (L2 hot) rather than kept live across the task above
 #pragma unroll
 					for (int j = 0; j < N; j++) {
@@ -557,7 +578,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 					}
 					joint_control_law<N, N, SPEC>(jt, NR, i, qj, dqj, pid, acc);
 				}
-		OSC_LS();
+		OSC_LS_K();
 				// Q_perp = H_1..H_R [0; I],  W = L^-T Q_perp,  K = L Q_perp
 				double Qp[N][Mn], W[N][Mn], K[N][Mn];
 #pragma unroll
@@ -595,7 +616,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				// ||N_prec||_F^2 = tr(G K^T K) must stay < 1e6 for the reference's 1e-3 range tolerance
 				if (!(nrm_chk < 1.0e6)) status |= OSC_STATUS_UNHANDLED;
 				cholesky_lower<Mn>(G, invg);
-		OSC_LS();
+		OSC_LS_K();
 				// u = W^T (qdd_d - M^-1 tau_prec)
 				double rhs[N];
 				if (P.use_prev_torques) {
@@ -696,7 +717,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	}
 
 #if defined(OSC_TRACE)
-	OSC_LS();
+	OSC_LS_K();
 #endif
 	// RobotController::computeControlTorques tail (RobotController.cpp:86-116)
 	if (P.torque_saturation) {

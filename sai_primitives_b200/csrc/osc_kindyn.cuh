@@ -431,17 +431,18 @@ DEVI void mass_matrix_s(const DevModel& m, KinDynS<N>& kd, const double* smt, in
 template <int N>
 constexpr int kSmAxes = 9 * N;
 
-// forward kinematics; qr[] holds the joint angles and is consumed (rotated) so that no run-time register index appears
+// forward kinematics; the joint angles are parked in the first slot of the orientation they produce (slot 9 i), so
+// that the loop reads them under its run-time index
 template <int N>
-DEVI void forward_kinematics_rolled(const DevModel& m, double (&qr)[N], double* smt, int sms) {
+DEVI void forward_kinematics_rolled(const DevModel& m, const double (&qr)[N], double* smt, int sms) {
 	double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 	double p[3] = {0, 0, 0};
+#pragma unroll
+	for (int i = 0; i < N; i++) smt[(size_t)(9 * i) * sms] = qr[i];
 #pragma unroll 1
 	for (int i = 0; i < N; i++) {
 		double s, c;
-		sincos_joint(qr[0], &s, &c);
-#pragma unroll
-		for (int k = 0; k + 1 < N; k++) qr[k] = qr[k + 1];
+		sincos_joint(smt[(size_t)(9 * i) * sms], &s, &c);
 		double t[3];
 		mat3_vec(R, m.t_fix[i], t);
 		p[0] += t[0];

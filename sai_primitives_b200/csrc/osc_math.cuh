@@ -86,33 +86,47 @@ DEVI double div_nz(double a, double b) {
 // of the reduced argument stays below 1e-19 |k|) and the minimax polynomials of fdlibm's __kernel_sin/__kernel_cos
 // on [-pi/4, pi/4]; larger arguments take the library routine.
 static __device__ __noinline__ void sincos_far(double x, double* sn, double* cs) { sincos(x, sn, cs); }
+// polynomial coefficients as constant-bank operands (a 64-bit immediate costs two moves per use)
+__constant__ double kSinCoef[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+									-1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};
+__constant__ double kCosCoef[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+									2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+__constant__ double kPio2[3] = {0.63661977236758134308, 1.57079632679489655800e+00, 6.12323399573676603587e-17};
 DEVI void sincos_joint(double x, double* sn, double* cs) {
 	if (!(fabs(x) < 1.0e4)) {
 		sincos_far(x, sn, cs);
 		return;
 	}
-	const int q = __double2int_rn(x * 0.63661977236758134308);
+	const int q = __double2int_rn(x * kPio2[0]);
 	const double k = (double)q;
-	double r = fma(-k, 1.57079632679489655800e+00, x);
-	r = fma(-k, 6.12323399573676603587e-17, r);
+	double r = fma(-k, kPio2[1], x);
+	r = fma(-k, kPio2[2], r);
 	const double z = r * r;
-	double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-	ps = fma(z, ps, 2.75573137070700676789e-06);
-	ps = fma(z, ps, -1.98412698298579493134e-04);
-	ps = fma(z, ps, 8.33333333332248946124e-03);
-	ps = fma(z, ps, -1.66666666666666324348e-01);
+	double ps = fma(z, kSinCoef[0], kSinCoef[1]);
+	ps = fma(z, ps, kSinCoef[2]);
+	ps = fma(z, ps, kSinCoef[3]);
+	ps = fma(z, ps, kSinCoef[4]);
+	ps = fma(z, ps, kSinCoef[5]);
 	const double s = fma(z * r, ps, r);
-	double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-	pc = fma(z, pc, -2.75573143513906633035e-07);
-	pc = fma(z, pc, 2.48015872894767294178e-05);
-	pc = fma(z, pc, -1.38888888888741095749e-03);
-	pc = fma(z, pc, 4.16666666666666019037e-02);
+	double pc = fma(z, kCosCoef[0], kCosCoef[1]);
+	pc = fma(z, pc, kCosCoef[2]);
+	pc = fma(z, pc, kCosCoef[3]);
+	pc = fma(z, pc, kCosCoef[4]);
+	pc = fma(z, pc, kCosCoef[5]);
 	const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
 	const double a = (q & 1) ? c : s;
 	const double b = (q & 1) ? s : c;
 	*sn = (q & 2) ? -a : a;
 	*cs = ((q + 1) & 2) ? -b : b;
 }
+
+// ---- asynchronous global -> shared copies of single doubles (LDGSTS): the data lands in this thread's shared-memory
+// slots without passing through registers, so a load can be issued thousands of cycles before its use
+DEVI void cp_async8(double* smem_dst, const double* gsrc) {
+	const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+DEVI void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // In-place Cholesky of the lower triangle of a symmetric positive definite matrix: A = L L^T.
 // invd[j] = 1 / L[j][j] is kept so that the triangular solves multiply instead of divide (one FP64 reciprocal

@@ -168,9 +168,20 @@ DEVI double pinv_gain(double k) { return (k > 1e-6) ? 1.0 / k : 0.0; }
 // identically zero (pure motion control of a full task), so that callers can skip it.
 // MOTION: the task is known (host check: mft_pure_motion) to be a full task under pure motion control without velocity
 // saturation, so only the two PID laws are compiled in.
+// sg != nullptr: the 24 goal components and the two motion integrators (30 doubles, components MC_GOAL_POS.. then
+// MC_INT_POS, MC_INT_ORI) were staged into shared memory (element e at sg[e * sgs]) by mft_stage_goals.
+template <typename IDX>
+DEVI void mft_stage_goals(const DevMft& t, IDX NR, IDX i, double* sg, int sgs) {
+	const double* st = t.st;
+#pragma unroll
+	for (int c = 0; c < 24; c++) cp_async8(sg + c * sgs, &ST(MC_GOAL_POS, c));
+#pragma unroll
+	for (int c = 0; c < 6; c++) cp_async8(sg + (24 + c) * sgs, &ST(MC_INT_POS, c));
+}
 template <bool MOTION = false, typename IDX = int64_t>
 DEVI bool mft_control_law(const DevMft& t, IDX NR, IDX i, const double x[3], const double R[9], const double v_in[3],
-						  const double w_in[3], bool write_observers, double fstar[6], double F[6], uint32_t& status) {
+						  const double w_in[3], bool write_observers, double fstar[6], double F[6], uint32_t& status,
+						  const double* sg = nullptr, int sgs = 0) {
 	double* st = t.st;
 	const osc_mft_params& p = t.p;
 	const double dt = t.dt;
@@ -186,13 +197,27 @@ DEVI bool mft_control_law(const DevMft& t, IDX NR, IDX i, const double x[3], con
 		}
 	}
 	double xd[3], Rd[9], vd[3], wd[3], ad[3], ald[3];
-	load3(st, NR, i, MC_GOAL_POS, xd);
+	if (MOTION && sg) {
+		cp_async_wait_all();
 #pragma unroll
-	for (int k = 0; k < 9; k++) Rd[k] = ST(MC_GOAL_ORI, k);
-	load3(st, NR, i, MC_GOAL_LINVEL, vd);
-	load3(st, NR, i, MC_GOAL_ANGVEL, wd);
-	load3(st, NR, i, MC_GOAL_LINACC, ad);
-	load3(st, NR, i, MC_GOAL_ANGACC, ald);
+		for (int k = 0; k < 3; k++) {
+			xd[k] = sg[(MC_GOAL_POS + k) * sgs];
+			vd[k] = sg[(MC_GOAL_LINVEL + k) * sgs];
+			wd[k] = sg[(MC_GOAL_ANGVEL + k) * sgs];
+			ad[k] = sg[(MC_GOAL_LINACC + k) * sgs];
+			ald[k] = sg[(MC_GOAL_ANGACC + k) * sgs];
+		}
+#pragma unroll
+		for (int k = 0; k < 9; k++) Rd[k] = sg[(MC_GOAL_ORI + k) * sgs];
+	} else {
+		load3(st, NR, i, MC_GOAL_POS, xd);
+#pragma unroll
+		for (int k = 0; k < 9; k++) Rd[k] = ST(MC_GOAL_ORI, k);
+		load3(st, NR, i, MC_GOAL_LINVEL, vd);
+		load3(st, NR, i, MC_GOAL_ANGVEL, wd);
+		load3(st, NR, i, MC_GOAL_LINACC, ad);
+		load3(st, NR, i, MC_GOAL_ANGACC, ald);
+	}
 
 	double ori_err_goal[3];
 	orientation_error(Rd, R, ori_err_goal);	 // :291-292 (desired == goal with OTG off)
@@ -202,8 +227,16 @@ DEVI bool mft_control_law(const DevMft& t, IDX NR, IDX i, const double x[3], con
 	if (MOTION || (t.full && p.force_space_dimension == 0 && p.moment_space_dimension == 0 && !p.closed_loop_force_control &&
 				   !p.closed_loop_moment_control)) {
 		double Ip[3], Io[3];
-		load3(st, NR, i, MC_INT_POS, Ip);
-		load3(st, NR, i, MC_INT_ORI, Io);
+		if (MOTION && sg) {
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				Ip[k] = sg[(24 + k) * sgs];
+				Io[k] = sg[(27 + k) * sgs];
+			}
+		} else {
+			load3(st, NR, i, MC_INT_POS, Ip);
+			load3(st, NR, i, MC_INT_ORI, Io);
+		}
 #pragma unroll
 		for (int k = 0; k < 3; k++) {
 			const double ex = x[k] - xd[k];
@@ -427,6 +460,39 @@ DEVI bool mft_control_law(const DevMft& t, IDX NR, IDX i, const double x[3], con
 
 // JointTask PID in task coordinates: returns t (pid "torques") and the desired acceleration.
 // e = S q - q_d etc.  (JointTask.cpp:299-346; Appendix C8: saturation loop uses the task dof)
+// staged variant: goals (position, velocity, acceleration), integrator, q and dq of the robot, 6 N doubles, copied to
+// shared memory ahead of time (element e at sg[e * sgs])
+template <int N, typename IDX>
+DEVI void joint_stage_goals(const DevJt& t, const double* qg, const double* dqg, IDX NR, IDX i, double* sg, int sgs) {
+	const double* st = t.st;
+#pragma unroll
+	for (int a = 0; a < N; a++) {
+		cp_async8(sg + a * sgs, &ST(JC_GOAL_POS, a));
+		cp_async8(sg + (N + a) * sgs, &ST(JC_GOAL_VEL, a));
+		cp_async8(sg + (2 * N + a) * sgs, &ST(JC_GOAL_ACC, a));
+		cp_async8(sg + (3 * N + a) * sgs, &ST(JC_INT, a));
+		cp_async8(sg + (4 * N + a) * sgs, qg + (IDX)a * NR + i);
+		cp_async8(sg + (5 * N + a) * sgs, dqg + (IDX)a * NR + i);
+	}
+}
+// full joint task without velocity saturation from the staged copy (the SPEC instantiation)
+template <int N, typename IDX>
+DEVI void joint_control_law_staged(const DevJt& t, IDX NR, IDX i, const double* sg, int sgs, double (&pid)[N], double (&acc)[N]) {
+	double* st = t.st;
+	const osc_joint_params& p = t.p;
+	cp_async_wait_all();
+	double I[N];
+#pragma unroll
+	for (int a = 0; a < N; a++) {
+		const double e = sg[(4 * N + a) * sgs] - sg[a * sgs];
+		acc[a] = sg[(2 * N + a) * sgs];
+		I[a] = sg[(3 * N + a) * sgs] + e * t.dt;
+		pid[a] = -p.kp[a] * e - p.kv[a] * (sg[(5 * N + a) * sgs] - sg[(N + a) * sgs]) - p.ki[a] * I[a];
+	}
+#pragma unroll
+	for (int a = 0; a < N; a++) ST(JC_INT, a) = I[a];
+}
+
 template <int N, int K, bool SPEC = false, typename IDX = int64_t>  // SPEC: full selection, no velocity saturation (host check)
 DEVI void joint_control_law(const DevJt& t, IDX NR, IDX i, const double (&q)[N], const double (&dq)[N],
 							double (&pid)[K], double (&acc)[K]) {
