@@ -329,12 +329,33 @@ def gpu_arm(args):
     if (st & capi.STATUS_UNHANDLED).any() or not np.isfinite(tau_host).all():
         raise SystemExit("bench: robots left the CUDA fast path (%d unhandled)" % int(((st & capi.STATUS_UNHANDLED) != 0).sum()))
 
+    # ---- same device-resident cycles with every controller instance on its own stream: independent batches overlap on
+    # the GPU, which fills the SMs the last wave of a 65,536-robot launch leaves idle (reported as an extra, not as value)
+    for s_ in sets:
+        s_["robot"].setStream(0)          # back to the handle's own non-blocking stream
+    def step_own_stream(s_):
+        rc = lib.osc_step_async(s_["robot"].handle, C.c_void_p(s_["q"].data_ptr()), C.c_void_p(s_["dq"].data_ptr()),
+                                C.c_void_p(s_["tau"].data_ptr()), capi.OSC_MEM_DEVICE)
+        if rc != 0:
+            raise RuntimeError(lib.osc_last_error(s_["robot"].handle))
+    for w in range(n_sets):
+        step_own_stream(sets[w])
+    for s_ in sets:
+        s_["robot"].sync()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_own_stream(sets[k % n_sets])
+    for s_ in sets:
+        s_["robot"].sync()
+    multi_ms = 1e3 * (time.perf_counter() - t0)
+    barrier()
+
     # ---- end to end through the C ABI with pinned HOST buffers: every step copies q, dq host->device and tau
     # device->host inside the timed region.  The n_sets controller instances run on their own streams
     # (osc_step_async), so the copies of one instance overlap the kernels of the others; the region is closed by
     # osc_sync on every instance and timed on the host clock (several streams: no single CUDA-event bracket exists).
     for s_ in sets:
-        s_["robot"].setStream(0)          # back to the handle's own non-blocking stream
         s_["hq"] = torch.from_numpy(np.ascontiguousarray(q.T)).pin_memory()
         s_["hdq"] = torch.from_numpy(np.ascontiguousarray(dq.T)).pin_memory()
         s_["htau"] = torch.zeros((n, R), dtype=torch.float64).pin_memory()
@@ -367,9 +388,9 @@ def gpu_arm(args):
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_ms, multi_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
+        total_ms, e2e_ms, multi_ms = float(t[0]), float(t[1]), float(t[2])
     value = world * R * args.steps / (total_ms * 1e-3)
     e2e_value = world * R * e2e_steps / (e2e_ms * 1e-3)
 
@@ -384,6 +405,13 @@ def gpu_arm(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if int(tr.get("robots", 0)) == R:
+                traffic = {"bytes_per_launch": tr["dram_bytes_per_launch"], "source": tr["source"]}
+        except Exception:
+            pass
         bytes_per_cycle = 8 * (14 + 24 + 21 + 2 * 13 + 7 + 12)   # q,dq + goals + integrators r/w + tau + pose observers
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -399,11 +427,13 @@ def gpu_arm(args):
                            "max": float(per_step_ms.max()), "samples": int(per_step_ms.size), "what": "CUDA events around one batched cycle, rank 0"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * n * R * 8), "d2h_bytes_per_step": int(n * R * 8),
                     "steps": e2e_steps, "checksum": checksum},
+            "extra": {"device_resident_one_stream_per_instance": {"value": world * R * args.steps / (multi_ms * 1e-3), "unit": UNIT,
+                      "what": "same cycles, the %d controller instances on their own streams (independent batches overlap), host clock" % n_sets}},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / FP64_PEAK_TFLOPS, "traffic": None,
-                         "kernel": "osc_cycle_kernel<7,6,true>", "kernel_ms": kernel_ms,
+                         "frac": achieved_tflops / FP64_PEAK_TFLOPS, "traffic": traffic,
+                         "kernel": "osc_cycle_kernel<7,6,JT,FULL,SPEC>", "kernel_ms": kernel_ms,
                          "flop_per_robot_cycle": FLOP_PER_CYCLE,
                          "peak_source": "datasheet-derived FP64 FMA peak (148 SM x 64 FMA/clk x 2 x 1.965 GHz); MEASURED_PEAKS.json has no FP64 entry",
                          "hbm": {"achieved_gbs": bytes_per_cycle * R / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,

@@ -122,6 +122,48 @@ DEVI void reduce_task_vector(const DevMft& t, const double (&v6)[6], double (&y)
 	}
 }
 
+// One bulk prefetch (cp.async.bulk.prefetch.L2) per state component for the robots of block `blk`: they are contiguous
+// in every component row, so thread k asks for row k of the list below -- one instruction per thread instead of one
+// prefetch per thread and component.
+template <int N, int R, bool HAS_JT>
+DEVI void prefetch_block_rows(const OscProgram& P, uint64_t blk) {
+	const uint64_t nrl = (uint64_t)P.n_robots;
+	const uint64_t b0 = blk * blockDim.x;
+	if (b0 >= nrl) return;
+	const uint32_t cnt = (uint32_t)((nrl - b0 < (uint64_t)blockDim.x) ? (nrl - b0) : (uint64_t)blockDim.x);
+	int k = threadIdx.x;
+	const char* row = nullptr;
+	uint32_t esz = 8;
+	if (k < N) {
+		row = (const char*)(P.q + (uint64_t)k * nrl);
+	} else if ((k -= N) < N) {
+		row = (const char*)(P.dq + (uint64_t)k * nrl);
+	} else {
+		k -= N;
+		if constexpr (R > 0) {
+			const DevMft& t = P.mft[0];
+			if (k >= 0 && k < 24) row = (const char*)(t.st + (uint64_t)k * nrl);
+			else if (k >= 24 && k < 30) row = (const char*)(t.st + (uint64_t)(MC_INT_POS + k - 24) * nrl);
+			else if (k == 30) { row = (const char*)(t.ist + (uint64_t)MI_N_TYPES * nrl); esz = 4; }
+			k -= 31;
+		}
+		if constexpr (HAS_JT || R == 0) {
+			const DevJt& jt = P.jt[0];
+			if (k >= 0 && k < 4 * N) {
+				const int grp = k / N, c = k - grp * N;
+				const int comp = (grp == 0 ? JC_GOAL_POS : grp == 1 ? JC_GOAL_VEL : grp == 2 ? JC_GOAL_ACC : JC_INT) + c;
+				row = (const char*)(jt.st + (uint64_t)comp * nrl);
+			}
+		}
+	}
+	if (row) {
+		const uint64_t a0 = (uint64_t)(row + b0 * esz);
+		const uint64_t a = a0 & ~(uint64_t)15;
+		const uint32_t bytes = (uint32_t)((a0 - a) + (uint64_t)cnt * esz) & ~15u;  // stays inside the row's allocation
+		if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
+	}
+}
+
 // Signature <N, R, HAS_JT, FULL>:  R = rank of a leading MotionForceTask (0: none), FULL = that task controls all six
 // directions (B = I), HAS_JT = a full JointTask closes the hierarchy.
 // Dynamic shared memory: cycle_smem_doubles<N, R>() doubles per thread,
@@ -154,20 +196,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	// end of the batch and robots handed to the general path keep computing on valid data but touch no state.
 	bool alive = i_raw < NR;
 	const IDX i = alive ? i_raw : NR - 1;
-#if defined(OSC_MODEL_IN_SMEM)
-	// Model constants from shared memory (broadcast LDS into ordinary registers, freely hoisted by the scheduler)
-	// instead of the constant bank (LDCU into the few uniform registers, consumed in place).
-	__shared__ __align__(16) unsigned char s_model[sizeof(DevModel)];
-	{
-		const int4* src = reinterpret_cast<const int4*>(&P.model);
-		int4* dst = reinterpret_cast<int4*>(s_model);
-		for (int k = threadIdx.x; k < (int)(sizeof(DevModel) / sizeof(int4)); k += blockDim.x) dst[k] = src[k];
-		__syncthreads();
-	}
-	const DevModel& mdl = *reinterpret_cast<const DevModel*>(s_model);
-#else
 	const DevModel& mdl = P.model;
-#endif
 	double* smt = sm + threadIdx.x;
 	constexpr int sms = kCycleBlock;  // the launcher always uses kCycleBlock threads per block
 
@@ -176,45 +205,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	// while the previous kernel of the stream is still running (programmatic dependent launch) uses the wait for it.
 	// Prefetches are safe ahead of griddepcontrol.wait: they only move lines into L2, which stays coherent.
 #ifndef OSC_NO_PREFETCH
-	{
-		// one bulk prefetch (cp.async.bulk.prefetch.L2) per state component and block: the block's robots are contiguous
-		// in every component row, so thread k asks for row k of the list below -- one instruction per thread instead of
-		// one prefetch per thread and component
-		const uint64_t nrl = (uint64_t)P.n_robots;
-		const uint64_t b0 = (uint64_t)blockIdx.x * blockDim.x;
-		const uint32_t cnt = (uint32_t)((nrl - b0 < (uint64_t)blockDim.x) ? (nrl - b0) : (uint64_t)blockDim.x);
-		int k = threadIdx.x;
-		const char* row = nullptr;
-		uint32_t esz = 8;
-		if (k < N) {
-			row = (const char*)(P.q + (uint64_t)k * nrl);
-		} else if ((k -= N) < N) {
-			row = (const char*)(P.dq + (uint64_t)k * nrl);
-		} else {
-			k -= N;
-			if constexpr (R > 0) {
-				const DevMft& t = P.mft[0];
-				if (k >= 0 && k < 24) row = (const char*)(t.st + (uint64_t)k * nrl);
-				else if (k >= 24 && k < 30) row = (const char*)(t.st + (uint64_t)(MC_INT_POS + k - 24) * nrl);
-				else if (k == 30) { row = (const char*)(t.ist + (uint64_t)MI_N_TYPES * nrl); esz = 4; }
-				k -= 31;
-			}
-			if constexpr (HAS_JT || R == 0) {
-				const DevJt& jt = P.jt[0];
-				if (k >= 0 && k < 4 * N) {
-					const int grp = k / N, c = k - grp * N;
-					const int comp = (grp == 0 ? JC_GOAL_POS : grp == 1 ? JC_GOAL_VEL : grp == 2 ? JC_GOAL_ACC : JC_INT) + c;
-					row = (const char*)(jt.st + (uint64_t)comp * nrl);
-				}
-			}
-		}
-		if (row) {
-			const uint64_t a0 = (uint64_t)(row + b0 * esz);
-			const uint64_t a = a0 & ~(uint64_t)15;
-			const uint32_t bytes = (uint32_t)((a0 - a) + (uint64_t)cnt * esz) & ~15u;  // stays inside the row's allocation
-			if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
-		}
-	}
+	prefetch_block_rows<N, R, HAS_JT>(P, blockIdx.x);
 #endif
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 	if (i_raw == 0 && P.sing_count) P.sing_count[P.sing_parity ^ 1] = 0;
