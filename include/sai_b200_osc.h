@@ -253,7 +253,9 @@ int osc_reinitialize_task(osc_handle* h, int task_id);
 /* ---- controller options (RobotController.h:66-76) ---- */
 int osc_enable_gravity_compensation(osc_handle* h, int enabled);
 int osc_enable_torque_saturation(osc_handle* h, int enabled);
-int osc_enable_joint_limit_avoidance(osc_handle* h, int enabled); /* enabled != 0 -> OSC_ERR_UNSUPPORTED */
+/* RobotController::enableJointLimitAvoidance (RobotController.h:70-72): JointLimitAvoidanceTask with its default zones
+ * and gains (JointLimitAvoidanceTask.h:26-35) blended into the torques as in RobotController.cpp:96-112. */
+int osc_enable_joint_limit_avoidance(osc_handle* h, int enabled);
 
 /* ---- the control cycle ---- */
 /* RobotController::updateControllerTaskModels (RobotController.cpp:68-77).  The task models are a pure function

@@ -947,10 +947,200 @@ class MotionForceTask:
         return self._singularity_handler.computeTorques(self._unit_mass_force, self._force_related_terms)
 
 
+class JointLimitAvoidanceTask:
+    """reference src/tasks/JointLimitAvoidanceTask.cpp:13-421: the constraint task that
+    RobotController owns.  Defaults: JointLimitAvoidanceTask.h:26-35.
+
+    Restatement decision: `_current_task_range = matrixRangeBasis(S N_prec)` with N_prec = I is the range basis of a
+    selection matrix, whose rows are orthonormal; Eigen's JacobiSVD performs no rotation on it, so the basis is the
+    identity (any other orthogonal basis would silently permute the avoidance torques in :417-419).  The identity is
+    used here and in the CUDA path."""
+
+    OFF, POS_Z1, POS_Z2, VEL_Z1, VEL_Z2 = range(5)
+    POSITIVE, NEGATIVE = 0, 1
+
+    def __init__(self, robot, task_name="joint_limit_avoidance_task"):
+        self._robot = robot
+        self._task_name = task_name
+        n = robot.dof()
+        self._enabled = True
+        self._kv = 20.0
+        self._position_z1_to_limit = 9 * math.pi / 180.0
+        self._position_z2_to_limit = 6 * math.pi / 180.0
+        self._velocity_z1_to_limit = 0.5
+        self._velocity_z2_to_limit = 0.3
+        self._max_torque_ratio_pos_limit = 1.0
+        self._max_torque_ratio_vel_limit = 0.05
+        self._limit_status = [self.OFF] * n
+        self._limit_direction = [self.POSITIVE] * n
+        self._limit_value = [0.0] * n
+        self._torque_limit_value = [0.0] * n
+        self._pos_valid = {}
+        self._vel_valid = {}
+        for lim in robot.jointLimits():                                   # verifyValidityPerJoint :95-118
+            self._pos_valid[lim.joint_index] = (lim.position_upper - lim.position_lower) > 2 * self._position_z1_to_limit
+            self._vel_valid[lim.joint_index] = lim.velocity > 2 * self._velocity_z1_to_limit
+        self._N_prec = np.eye(n)
+        self._N = np.zeros((n, n))
+        self._active_constraints = 0
+        self._joint_selection = np.zeros((0, n))
+        self.reInitializeTask()
+
+    def reInitializeTask(self):                                           # :120-122
+        self._computeJointSelectionMatrix()
+
+    def _updateLimitStatus(self):                                         # :174-243
+        fmax = np.finfo(np.float64).max
+        for lim in self._robot.jointLimits():
+            i = lim.joint_index
+            self._limit_status[i] = self.OFF
+            self._limit_direction[i] = self.POSITIVE
+            self._limit_value[i] = 0.0
+            self._torque_limit_value[i] = 0.0
+            q = self._robot.q()[i]
+            dq = self._robot.dq()[i]
+            pv, vv = self._pos_valid[i], self._vel_valid[i]
+            if pv and lim.position_upper != fmax:
+                if q > lim.position_upper - self._position_z1_to_limit:
+                    self._limit_direction[i] = self.POSITIVE
+                    self._limit_value[i] = lim.position_upper
+                    self._torque_limit_value[i] = lim.effort
+                    self._limit_status[i] = self.POS_Z1
+                if q > lim.position_upper - self._position_z2_to_limit:
+                    self._limit_status[i] = self.POS_Z2
+            if pv and lim.position_lower != -fmax:
+                if q < lim.position_lower + self._position_z1_to_limit:
+                    self._limit_direction[i] = self.NEGATIVE
+                    self._limit_value[i] = lim.position_lower
+                    self._torque_limit_value[i] = lim.effort
+                    self._limit_status[i] = self.POS_Z1
+                if q < lim.position_lower + self._position_z2_to_limit:
+                    self._limit_status[i] = self.POS_Z2
+            if vv and (self._limit_status[i] == self.OFF or self._limit_direction[i] == self.NEGATIVE):
+                if dq > lim.velocity - self._velocity_z1_to_limit:
+                    self._limit_direction[i] = self.POSITIVE
+                    self._limit_value[i] = lim.velocity
+                    self._torque_limit_value[i] = lim.effort
+                    self._limit_status[i] = self.VEL_Z1
+                if dq > lim.velocity - self._velocity_z2_to_limit:
+                    self._limit_status[i] = self.VEL_Z2
+            if vv and (self._limit_status[i] == self.OFF or self._limit_direction[i] == self.POSITIVE):
+                if dq < -lim.velocity + self._velocity_z1_to_limit:
+                    self._limit_direction[i] = self.NEGATIVE
+                    self._limit_value[i] = -lim.velocity
+                    self._torque_limit_value[i] = lim.effort
+                    self._limit_status[i] = self.VEL_Z1
+                if dq < -lim.velocity + self._velocity_z2_to_limit:
+                    self._limit_status[i] = self.VEL_Z2
+        self._active_constraints = sum(1 for s_ in self._limit_status if s_ != self.OFF)
+
+    def _computeJointSelectionMatrix(self):                               # :245-256
+        self._updateLimitStatus()
+        n = self._robot.dof()
+        S = np.zeros((self._active_constraints, n))
+        row = 0
+        for i in range(n):
+            if self._limit_status[i] != self.OFF:
+                S[row, i] = 1.0
+                row += 1
+        self._joint_selection = S
+
+    def updateTaskModel(self, N_prec):                                    # :124-172
+        n = self._robot.dof()
+        N_prec = np.asarray(N_prec, dtype=np.float64)
+        if N_prec.shape != (n, n):
+            raise ValueError("N_prec matrix size not consistent with robot dof in JointLimitAvoidanceTask::updateTaskModel")
+        if not self._enabled:
+            self._N = np.eye(n)
+            self._N_prec = np.eye(n)
+            return
+        self._N_prec = N_prec.copy()
+        self._computeJointSelectionMatrix()
+        self._projected_jacobian = self._joint_selection @ self._N_prec
+        if self._active_constraints == 0:                                 # range basis of an empty matrix: norm 0 (:161-166)
+            self._N = np.eye(n)
+            return
+        ops = self._robot.operationalSpaceMatrices(self._projected_jacobian)   # range basis = identity, see the class docstring
+        self._M_partial = ops.Lambda
+        self._N = ops.N
+
+    def getTaskAndPreviousNullspace(self):
+        return self._N @ self._N_prec
+
+    @staticmethod
+    def _blend(z, z1, z2, direction):                                     # computeBlendingCoefficient :16-37
+        if direction == JointLimitAvoidanceTask.NEGATIVE:
+            if z >= z1:
+                return 0.0
+            if z <= z2:
+                return 1.0
+            return (z1 - z) / (z1 - z2)
+        if z <= z1:
+            return 0.0
+        if z >= z2:
+            return 1.0
+        return (z - z1) / (z2 - z1)
+
+    def computeTorques(self, tau_tasks=None):                             # :258-421
+        n = self._robot.dof()
+        if tau_tasks is None:
+            tau_tasks = np.zeros(n)
+        if not self._enabled or self._active_constraints == 0:
+            return np.zeros(n)
+        q, dq = self._robot.q(), self._robot.dq()
+        kv = self._kv
+        pz1, pz2, vz1, vz2 = self._position_z1_to_limit, self._position_z2_to_limit, self._velocity_z1_to_limit, self._velocity_z2_to_limit
+        rp, rv = self._max_torque_ratio_pos_limit, self._max_torque_ratio_vel_limit
+        out = np.zeros(self._active_constraints)
+        c = 0
+        for i in range(n):
+            st, d, lv, tl = self._limit_status[i], self._limit_direction[i], self._limit_value[i], self._torque_limit_value[i]
+            clampv = lambda x: max(min(x, tl * rv), -tl * rv)
+            if d == self.POSITIVE:
+                if st == self.POS_Z1:
+                    a = self._blend(q[i], lv - pz1, lv - pz2, d)
+                    t1 = tau_tasks[i] - kv * dq[i]
+                    out[c] = (1 - a) * tau_tasks[i] + a * t1
+                elif st == self.POS_Z2:
+                    a = self._blend(q[i], lv - pz2, lv, d)
+                    t1 = tau_tasks[i] - kv * dq[i]
+                    t2 = -tl * rp - kv * dq[i]
+                    out[c] = (1 - a) * t1 + a * t2
+                elif st == self.VEL_Z1:
+                    a = self._blend(dq[i], lv - vz1, lv - vz2, d)
+                    t1 = -kv * dq[i]
+                    out[c] = (1 - a) * tau_tasks[i] + a * t1
+                elif st == self.VEL_Z2:
+                    a = self._blend(dq[i], lv - vz2, lv, d)
+                    t1 = clampv(-kv * dq[i])
+                    t2 = -a * tl * rv
+                    out[c] = (1 - a) * t1 + a * t2
+            else:
+                if st == self.POS_Z1:
+                    a = self._blend(q[i], lv + pz1, lv + pz2, d)
+                    t1 = clampv(tau_tasks[i] - kv * dq[i])
+                    out[c] = a * tau_tasks[i] + (1 - a) * t1                 # sic (:344-345)
+                elif st == self.POS_Z2:
+                    a = self._blend(q[i], lv + pz2, lv, d)
+                    t1 = tau_tasks[i] - kv * dq[i]
+                    t2 = tl * rp - kv * dq[i]
+                    out[c] = (1 - a) * t1 + a * t2
+                elif st == self.VEL_Z1:
+                    a = self._blend(dq[i], lv + vz1, lv + vz2, d)
+                    t1 = clampv(-kv * dq[i])
+                    out[c] = (1 - a) * tau_tasks[i] + a * t1
+                elif st == self.VEL_Z2:
+                    a = self._blend(dq[i], lv + vz2, lv, d)
+                    t1 = clampv(-kv * dq[i])
+                    t2 = tl * rv
+                    out[c] = (1 - a) * t1 + a * t2
+            if st != self.OFF:
+                c += 1
+        return self._projected_jacobian.T @ out                           # range basis = identity
+
+
 class RobotController:
-    """reference src/RobotController.cpp:8-118.  Joint-limit avoidance
-    (JointLimitAvoidanceTask) is SURVEY.md row f-2 and not restated: enabling it
-    raises."""
+    """reference src/RobotController.cpp:8-118, including the joint-limit avoidance blend (:96-112)."""
 
     def __init__(self, robot: SaiModel, tasks):
         if len(tasks) == 0:
@@ -975,6 +1165,8 @@ class RobotController:
                 raise ValueError("task [%s] cannot be added: it is in the nullspace of a full joint task" % task.getTaskName())
             if task.task_type == "joint" and task.isFullJointTask():
                 cannot_accept_new_tasks = True
+        self._joint_limit_avoidance_task = JointLimitAvoidanceTask(robot)
+        self._N_constraints = np.eye(robot.dof())
         self._torque_limits = np.full(robot.dof(), np.finfo(np.float64).max)
         for lim in robot.jointLimits():                           # :61-65
             self._torque_limits[lim.joint_index] = lim.effort
@@ -982,13 +1174,13 @@ class RobotController:
     def enableGravityCompensation(self, f): self._enable_gravity_compensation = bool(f)
     def enableTorqueSaturation(self, f): self._enable_torque_saturation = bool(f)
 
-    def enableJointLimitAvoidance(self, f):
-        if f:
-            raise NotImplementedError("JointLimitAvoidanceTask is out of scope (SURVEY.md f-2)")
+    def enableJointLimitAvoidance(self, f): self._enable_joint_limit_avoidance = bool(f)
 
     def updateControllerTaskModels(self):                         # :68-77
         n = self._robot.dof()
         N_prec = np.eye(n)
+        self._joint_limit_avoidance_task.updateTaskModel(N_prec)  # always, as in the reference (:71)
+        self._N_constraints = self._joint_limit_avoidance_task.getTaskAndPreviousNullspace()
         for task in self._tasks:
             task.updateTaskModel(N_prec)
             N_prec = task.getTaskAndPreviousNullspace()
@@ -1000,10 +1192,16 @@ class RobotController:
             control_torques = control_torques + task.computeTorques(control_torques)
         if self._enable_torque_saturation:
             control_torques = np.clip(control_torques, -self._torque_limits, self._torque_limits)
+        if self._enable_joint_limit_avoidance:                    # :96-112
+            jla = self._joint_limit_avoidance_task.computeTorques(control_torques)
+            control_torques = jla + self._N_constraints.T @ control_torques
+            if self._enable_torque_saturation:
+                control_torques = np.clip(control_torques, -self._torque_limits, self._torque_limits)
         if self._enable_gravity_compensation:
             control_torques = control_torques + self._robot.jointGravityVector()
         return control_torques
 
     def reinitializeTasks(self):                                  # :120-125
+        self._joint_limit_avoidance_task.reInitializeTask()
         for task in self._tasks:
             task.reInitializeTask()

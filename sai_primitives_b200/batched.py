@@ -7,8 +7,7 @@ numpy arrays of shape [n_robots, ncomp] (a single vector of ncomp values is broa
 all robots) or, for zero-copy use, raw device pointers in the SoA layout of the C ABI.
 
 Differences from the reference, by design (BASELINE.json north_star):
-  * internal OTG does not exist on this path (reference default is ON): enabling it raises;
-  * JointLimitAvoidanceTask is not part of the path: enabling it raises.
+  * internal OTG does not exist on this path (reference default is ON): enabling it raises.
 """
 from __future__ import annotations
 

@@ -22,6 +22,18 @@ cudaError_t launch_reinit_mft(const OscProgram& P, int mft_index, int full_init,
 	DISPATCH_N(P.model.n, (reinit_mft_kernel<N_><<<grid_for(P.n_robots, 128), 128, 0, stream>>>(P, mft_index, full_init)));
 	return cudaGetLastError();
 }
+cudaError_t launch_jla(const OscProgram& P, cudaStream_t stream) {
+	DevJla jp;	// JointLimitAvoidanceTask.h:26-35
+	jp.kv = 20.0;
+	jp.position_z1_to_limit = 9.0 * 3.14159265358979323846 / 180.0;
+	jp.position_z2_to_limit = 6.0 * 3.14159265358979323846 / 180.0;
+	jp.velocity_z1_to_limit = 0.5;
+	jp.velocity_z2_to_limit = 0.3;
+	jp.max_torque_ratio_pos_limit = 1.0;
+	jp.max_torque_ratio_vel_limit = 0.05;
+	DISPATCH_N(P.model.n, (jla_kernel<N_><<<grid_for(P.n_robots, 128), 128, 0, stream>>>(P, jp)));
+	return cudaGetLastError();
+}
 cudaError_t launch_reinit_jt(const OscProgram& P, int jt_index, cudaStream_t stream) {
 	DISPATCH_N(P.model.n, (reinit_jt_kernel<N_><<<grid_for(P.n_robots, 128), 128, 0, stream>>>(P, jt_index)));
 	return cudaGetLastError();

@@ -164,5 +164,188 @@ __global__ void eval_model_kernel(const __grid_constant__ OscProgram P, osc_link
 		for (int j = 0; j < N; j++) out.g[(int64_t)j * NR + i] = kd.g[j];
 }
 
+// ------------------------------------------------------------------------------------------------
+// JointLimitAvoidanceTask + the blend of RobotController::computeControlTorques, one robot per
+// thread, applied to the torques the cycle kernels left in P.tau:
+//   limit status per joint            JointLimitAvoidanceTask::updateLimitStatus          JointLimitAvoidanceTask.cpp:174-243
+//   N_constraints = I - M^-1 S^T (S M^-1 S^T)^-1 S   updateTaskModel with N_prec = I      :124-172, RobotController.cpp:71-72
+//   avoidance torques per active joint computeTorques                                     :258-421
+//   tau <- S^T t + N_constraints^T tau, saturation, gravity                               RobotController.cpp:96-116
+// S selects the k joints inside a buffer zone.  Instead of compacting them (run-time indices), the k x k block
+// (M^-1)_AA is embedded in an n x n matrix with the identity on the inactive joints; its inverse carries
+// (S M^-1 S^T)^-1 on the active block.  Robots with no active joint (the common case) only pay the status test.
+DEVI double jla_blend(double z, double z1, double z2, bool negative) {	// computeBlendingCoefficient :16-37
+	if (negative) {
+		if (z >= z1) return 0.0;
+		if (z <= z2) return 1.0;
+		return (z1 - z) / (z1 - z2);
+	}
+	if (z <= z1) return 0.0;
+	if (z >= z2) return 1.0;
+	return (z - z1) / (z2 - z1);
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) jla_kernel(const __grid_constant__ OscProgram P, DevJla jp) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t NR = P.n_robots;
+	if (i >= NR) return;
+	if (P.status[i] & OSC_STATUS_UNHANDLED) return;	 // NaN torques stay NaN
+	const DevModel& m = P.model;
+	enum { OFF = 0, POS_Z1, POS_Z2, VEL_Z1, VEL_Z2 };
+	double q[N], dq[N], tau[N];
+	int st[N];
+	bool neg[N];
+	double lv[N];
+	int k = 0;
+	const double fmax = 1.7976931348623157e308;
+#pragma unroll
+	for (int j = 0; j < N; j++) {
+		q[j] = P.q[(int64_t)j * NR + i];
+		dq[j] = P.dq[(int64_t)j * NR + i];
+		tau[j] = P.tau[(int64_t)j * NR + i];
+		const bool pos_valid = (m.q_upper[j] - m.q_lower[j]) > 2.0 * jp.position_z1_to_limit;	// verifyValidityPerJoint :95-118
+		const bool vel_valid = m.dq_max[j] > 2.0 * jp.velocity_z1_to_limit;
+		int s = OFF;
+		bool ng = false;
+		double v = 0.0;
+		if (pos_valid && m.q_upper[j] != fmax) {
+			if (q[j] > m.q_upper[j] - jp.position_z1_to_limit) {
+				ng = false;
+				v = m.q_upper[j];
+				s = POS_Z1;
+			}
+			if (q[j] > m.q_upper[j] - jp.position_z2_to_limit) s = POS_Z2;
+		}
+		if (pos_valid && m.q_lower[j] != -fmax) {
+			if (q[j] < m.q_lower[j] + jp.position_z1_to_limit) {
+				ng = true;
+				v = m.q_lower[j];
+				s = POS_Z1;
+			}
+			if (q[j] < m.q_lower[j] + jp.position_z2_to_limit) s = POS_Z2;
+		}
+		if (vel_valid && (s == OFF || ng)) {
+			if (dq[j] > m.dq_max[j] - jp.velocity_z1_to_limit) {
+				ng = false;
+				v = m.dq_max[j];
+				s = VEL_Z1;
+			}
+			if (dq[j] > m.dq_max[j] - jp.velocity_z2_to_limit) s = VEL_Z2;
+		}
+		if (vel_valid && (s == OFF || !ng)) {
+			if (dq[j] < -m.dq_max[j] + jp.velocity_z1_to_limit) {
+				ng = true;
+				v = -m.dq_max[j];
+				s = VEL_Z1;
+			}
+			if (dq[j] < -m.dq_max[j] + jp.velocity_z2_to_limit) s = VEL_Z2;
+		}
+		st[j] = s;
+		neg[j] = ng;
+		lv[j] = v;
+		k += (s != OFF) ? 1 : 0;
+	}
+	if (k == 0 && !P.gravity_comp) return;
+
+	KinDyn<N> kd;
+	forward_kinematics<N>(m, q, kd);
+	if (P.gravity_comp)
+		mass_matrix<N, true>(m, kd);
+	else
+		mass_matrix<N, false>(m, kd);
+	if (k > 0) {
+		// avoidance torque of every active joint (:279-412)
+		double t[N];
+		const double pz1 = jp.position_z1_to_limit, pz2 = jp.position_z2_to_limit, vz1 = jp.velocity_z1_to_limit, vz2 = jp.velocity_z2_to_limit;
+#pragma unroll
+		for (int j = 0; j < N; j++) {
+			const double tl = m.effort[j], cap = tl * jp.max_torque_ratio_vel_limit;
+			const double damp = -jp.kv * dq[j];
+			double dc = damp;
+			dc = dc > cap ? cap : dc;
+			dc = dc < -cap ? -cap : dc;
+			double out = 0.0;
+			if (!neg[j]) {
+				if (st[j] == POS_Z1) {
+					const double a = jla_blend(q[j], lv[j] - pz1, lv[j] - pz2, false);
+					out = (1.0 - a) * tau[j] + a * (tau[j] + damp);
+				} else if (st[j] == POS_Z2) {
+					const double a = jla_blend(q[j], lv[j] - pz2, lv[j], false);
+					out = (1.0 - a) * (tau[j] + damp) + a * (-tl * jp.max_torque_ratio_pos_limit + damp);
+				} else if (st[j] == VEL_Z1) {
+					const double a = jla_blend(dq[j], lv[j] - vz1, lv[j] - vz2, false);
+					out = (1.0 - a) * tau[j] + a * damp;
+				} else if (st[j] == VEL_Z2) {
+					const double a = jla_blend(dq[j], lv[j] - vz2, lv[j], false);
+					out = (1.0 - a) * dc + a * (-a * cap);
+				}
+			} else {
+				if (st[j] == POS_Z1) {
+					const double a = jla_blend(q[j], lv[j] + pz1, lv[j] + pz2, true);
+					double t1 = tau[j] + damp;
+					t1 = t1 > cap ? cap : t1;
+					t1 = t1 < -cap ? -cap : t1;
+					out = a * tau[j] + (1.0 - a) * t1;	// sic (:344-345)
+				} else if (st[j] == POS_Z2) {
+					const double a = jla_blend(q[j], lv[j] + pz2, lv[j], true);
+					out = (1.0 - a) * (tau[j] + damp) + a * (tl * jp.max_torque_ratio_pos_limit + damp);
+				} else if (st[j] == VEL_Z1) {
+					const double a = jla_blend(dq[j], lv[j] + vz1, lv[j] + vz2, true);
+					out = (1.0 - a) * tau[j] + a * dc;
+				} else if (st[j] == VEL_Z2) {
+					const double a = jla_blend(dq[j], lv[j] + vz2, lv[j], true);
+					out = (1.0 - a) * dc + a * cap;
+				}
+			}
+			t[j] = out;
+		}
+		// N_constraints^T tau = tau - S^T (S M^-1 S^T)^-1 S M^-1 tau
+		double L[N][N], invd[N];
+#pragma unroll
+		for (int r = 0; r < N; r++)
+#pragma unroll
+			for (int c = 0; c < N; c++) L[r][c] = kd.M[r][c];
+		cholesky_lower<N>(L, invd);
+		double y[N];
+#pragma unroll
+		for (int j = 0; j < N; j++) y[j] = tau[j];
+		solve_spd<N>(L, invd, y);
+		double B[N][N], invb[N];
+#pragma unroll
+		for (int a = 0; a < N; a++) {
+			double col[N];
+#pragma unroll
+			for (int r = 0; r < N; r++) col[r] = (r == a) ? 1.0 : 0.0;
+			if (st[a] != OFF) solve_spd<N>(L, invd, col);
+#pragma unroll
+			for (int r = 0; r < N; r++) B[r][a] = (st[a] != OFF && st[r] != OFF) ? col[r] : ((r == a) ? 1.0 : 0.0);
+		}
+		cholesky_lower<N>(B, invb);
+		double z[N];
+#pragma unroll
+		for (int j = 0; j < N; j++) z[j] = (st[j] != OFF) ? y[j] : 0.0;
+		solve_spd<N>(B, invb, z);
+#pragma unroll
+		for (int j = 0; j < N; j++)
+			if (st[j] != OFF) tau[j] = t[j] + tau[j] - z[j];
+		if (P.torque_saturation) {
+#pragma unroll
+			for (int j = 0; j < N; j++) {
+				if (tau[j] > m.effort[j])
+					tau[j] = m.effort[j];
+				else if (tau[j] < -m.effort[j])
+					tau[j] = -m.effort[j];
+			}
+		}
+	}
+	if (P.gravity_comp) {
+#pragma unroll
+		for (int j = 0; j < N; j++) tau[j] += kd.g[j];
+	}
+#pragma unroll
+	for (int j = 0; j < N; j++) P.tau[(int64_t)j * NR + i] = tau[j];
+}
+
 #undef ST
 }  // namespace osc

@@ -36,6 +36,7 @@ struct osc_handle {
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	bool finalized = false;
 	bool models_armed = false;
+	bool jla_enabled = false;  // RobotController::enableJointLimitAvoidance
 	int sig_R = 0;
 	bool sig_jt = false;
 	std::vector<TaskInfo> tasks;
@@ -231,6 +232,7 @@ void build_dev_model(const osc_model_desc& m, DevModel& d) {
 		d.q_lower[i] = m.q_lower[i];
 		d.q_upper[i] = m.q_upper[i];
 		d.effort[i] = m.effort[i];
+		d.dq_max[i] = m.dq_max[i];
 	}
 	std::memcpy(d.gravity, m.gravity_world, sizeof(double) * 3);
 }
@@ -959,8 +961,7 @@ int osc_enable_torque_saturation(osc_handle* h, int enabled) {
 }
 int osc_enable_joint_limit_avoidance(osc_handle* h, int enabled) {
 	ENTER(h);
-	if (enabled)
-		return fail(h, OSC_ERR_UNSUPPORTED, "JointLimitAvoidanceTask is outside the accelerated path (SURVEY.md section 8, row f-2)");
+	h->jla_enabled = enabled != 0;
 	return OSC_OK;
 }
 
@@ -978,7 +979,18 @@ static int run_cycle(osc_handle* h, double* tau_out, int mem_kind, bool sync_hos
 	h->prog.tau = (mem_kind == OSC_MEM_DEVICE) ? tau_out : h->d_tau;
 	h->prog.update_models = h->models_armed ? 1 : 0;
 	h->models_armed = false;
-	cudaError_t e = osc::launch_cycle(h->model.n, h->sig_R, h->sig_jt, h->prog, h->stream);
+	cudaError_t e;
+	if (h->jla_enabled) {
+		// RobotController.cpp:96-116: the avoidance blend comes after the task torques (and their saturation) and before
+		// gravity compensation, so the cycle kernels leave gravity to the avoidance kernel
+		OscProgram prog = h->prog;
+		prog.gravity_comp = 0;
+		e = osc::launch_cycle(h->model.n, h->sig_R, h->sig_jt, prog, h->stream);
+		if (e == cudaSuccess) e = osc::launch_jla(h->prog, h->stream);
+		if (e == cudaSuccess) h->launches += 1;
+	} else {
+		e = osc::launch_cycle(h->model.n, h->sig_R, h->sig_jt, h->prog, h->stream);
+	}
 	if (e == cudaErrorNotSupported) return fail(h, OSC_ERR_UNSUPPORTED, "no kernel compiled for this hierarchy signature");
 	CUDA_TRY(h, e);
 	h->launches += (h->sig_R > 0) ? 2 : 1;  // fused cycle kernel (+ the SVD-path kernel when a motion-force task leads)

@@ -65,7 +65,7 @@ struct DevModel {
 	double mass[OSC_MAX_DOF];
 	double com[OSC_MAX_DOF][3];
 	double inertia[OSC_MAX_DOF][6];	 // xx xy xz yy yz zz
-	double q_lower[OSC_MAX_DOF], q_upper[OSC_MAX_DOF], effort[OSC_MAX_DOF];
+	double q_lower[OSC_MAX_DOF], q_upper[OSC_MAX_DOF], effort[OSC_MAX_DOF], dq_max[OSC_MAX_DOF];
 	double gravity[3];	// world frame
 };
 
@@ -93,6 +93,14 @@ struct DevJt {
 	double dt;
 	osc_joint_params p;
 	double* st;	 // JC_COUNT x N
+};
+
+// JointLimitAvoidanceTask parameters (JointLimitAvoidanceTask.h:26-35; the reference has no setters for them)
+struct DevJla {
+	double kv;
+	double position_z1_to_limit, position_z2_to_limit;
+	double velocity_z1_to_limit, velocity_z2_to_limit;
+	double max_torque_ratio_pos_limit, max_torque_ratio_vel_limit;
 };
 
 struct DevTask {

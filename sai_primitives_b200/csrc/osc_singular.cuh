@@ -119,7 +119,8 @@ static __device__ __noinline__ void svd_thin(const double* A, int m, int n, doub
 					be += W[i * wc + q] * W[i * wc + q];
 					ga += W[i * wc + p] * W[i * wc + q];
 				}
-				if (ga == 0.0 || fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
+				// stop at the rounding floor of the rotations (a 1e-16 threshold is below it and never met: all 40 sweeps ran)
+				if (ga == 0.0 || fabs(ga) <= 2e-15 * sqrt(al * be)) continue;
 				rotated = true;
 				const double zeta = (be - al) / (2.0 * ga);
 				const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));

@@ -125,8 +125,65 @@ def test_config2_gravity_and_saturation():
     ref = ob.cycle()
     assert (robot.status() & sp.capi.STATUS_UNHANDLED).sum() == 0
     assert rel_err(tau, ref).max() < REL_TOL
-    with pytest.raises(NotImplementedError):
-        ctrl.enableJointLimitAvoidance(True)
+
+
+def _states_near_limits(robot_name, N, seed_stream=11):
+    """states with a few joints pushed into the position / velocity buffer zones (both zones, both directions)"""
+    from oracle.robots import make_chain
+    ch = make_chain(robot_name)
+    q, dq, _ = sample_states(robot_name, N, min_sigma_ratio=0.075)
+    expect_active = np.zeros(N, dtype=int)
+    for i in range(N):
+        g = rng_for(i, stream=seed_stream)
+        for _ in range(int(g.integers(0, 4))):          # 0..3 joints per robot
+            j = int(g.integers(0, ch.n)); kind = int(g.integers(0, 4)); depth = g.uniform(0.005, 0.15)
+            if kind == 0: q[i, j] = ch.q_upper[j] - depth
+            elif kind == 1: q[i, j] = ch.q_lower[j] + depth
+            elif kind == 2: dq[i, j] = ch.dq_max[j] - 3.0 * depth
+            else: dq[i, j] = -ch.dq_max[j] + 3.0 * depth
+    return q, dq
+
+
+@pytest.mark.parametrize("hier", ["jt", "mft_jt"])
+@pytest.mark.parametrize("sat,grav", [(False, False), (True, True)])
+def test_joint_limit_avoidance(hier, sat, grav):
+    """SURVEY.md row f-2: RobotController::enableJointLimitAvoidance (RobotController.cpp:96-112) with the zone logic of
+    JointLimitAvoidanceTask.cpp:174-421, on states inside the position and velocity buffer zones."""
+    import sai_primitives_b200 as sp
+    N = 96
+    q, dq = _states_near_limits("panda", N)
+    robot = sp.BatchedRobot("panda", N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    link, pt = TASK_POINTS["panda"]
+    ob = OracleBatch("panda", N); ob.set_state(q, dq)
+    tasks = []
+    if hier == "mft_jt":
+        mft = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt))); tasks.append(mft)
+        omft = ob.add_mft(link, (np.eye(3), np.array(pt)))
+    jt = sp.JointTask(robot); tasks.append(jt)
+    ojt = ob.add_jt()
+    ctrl = sp.RobotController(robot, tasks)
+    ctrl.enableJointLimitAvoidance(True); ctrl.enableGravityCompensation(grav); ctrl.enableTorqueSaturation(sat)
+    ob.finalize()
+    for c in ob.controllers:
+        c.enableJointLimitAvoidance(True); c.enableGravityCompensation(grav); c.enableTorqueSaturation(sat)
+    if hier == "mft_jt":
+        _set_mft_goals(mft, omft, N)
+    _set_joint_goals(jt, ojt, q, 7)
+    ctrl.updateControllerTaskModels()
+    tau = ctrl.computeControlTorques()
+    ref = ob.cycle()
+    active = np.array([c._joint_limit_avoidance_task._active_constraints for c in ob.controllers])
+    assert (active > 0).sum() > N // 3 and (active == 0).sum() > 5 and active.max() >= 2
+    st = robot.status()
+    assert (st & sp.capi.STATUS_UNHANDLED).sum() == 0
+    assert rel_err(tau, ref).max() < REL_TOL
+    # switching it off again gives the plain controller back
+    ctrl.enableJointLimitAvoidance(False)
+    for c in ob.controllers:
+        c.enableJointLimitAvoidance(False)
+    ctrl.updateControllerTaskModels()
+    assert rel_err(ctrl.computeControlTorques(), ob.cycle()).max() < REL_TOL
 
 
 @pytest.mark.parametrize("dec", DEC)

@@ -114,3 +114,43 @@ def test_free_functions():
         orientationError(2 * np.eye(3), np.eye(3))
     K = np.diag([20.0, 0.0, 5.0])
     assert np.allclose(computePseudoInverse(K), np.diag([0.05, 0.0, 0.2]))
+
+
+def test_joint_limit_avoidance_oracle_properties():
+    """JointLimitAvoidanceTask restatement (reference JointLimitAvoidanceTask.cpp:124-421): status zones, the constraint
+    null space and the RobotController blend (RobotController.cpp:96-112)."""
+    from oracle import primitives as OP
+    from oracle.robots import make_chain
+    from oracle.sai_model import SaiModel
+    ch = make_chain("panda")
+    m = SaiModel(ch)
+    q = ch.q_lower + 0.5 * (ch.q_upper - ch.q_lower)
+    dq = np.zeros(ch.n)
+    q[3] = ch.q_upper[3] - 0.05          # inside zone 2 (6 deg = 0.1047)
+    q[1] = ch.q_lower[1] + 0.13          # inside zone 1 (9 deg = 0.157) only
+    dq[5] = ch.dq_max[5] - 0.2           # velocity zone 2 (0.3)
+    m.setQ(q); m.setDq(dq); m.updateModel()
+    jt = OP.JointTask(m)
+    c = OP.RobotController(m, [jt])
+    jt.setGoalPosition(q + 0.3)
+    c.updateControllerTaskModels()
+    plain = c.computeControlTorques()
+    c.enableJointLimitAvoidance(True)
+    c.updateControllerTaskModels()
+    tau = c.computeControlTorques()
+    jla = c._joint_limit_avoidance_task
+    assert jla._limit_status == [jla.OFF, jla.POS_Z1, jla.OFF, jla.POS_Z2, jla.OFF, jla.VEL_Z2, jla.OFF]
+    assert jla._limit_direction[1] == jla.NEGATIVE and jla._limit_direction[3] == jla.POSITIVE
+    S = jla._joint_selection
+    N = c._N_constraints
+    assert np.allclose(N @ N, N, atol=1e-12)                    # projector
+    assert np.allclose(S @ N, 0.0, atol=1e-12)                  # no acceleration of the constrained joints from the tasks
+    inactive = [0, 2, 4, 6]
+    assert np.allclose(tau[inactive], plain[inactive], atol=1e-12)   # N^T only touches the active joints' torques
+    assert tau[3] < plain[3]                                    # pushed away from the upper limit
+    # far from every limit the task does nothing
+    m.setQ(ch.q_lower + 0.5 * (ch.q_upper - ch.q_lower)); m.setDq(np.zeros(ch.n)); m.updateModel()
+    c.updateControllerTaskModels()
+    a = c.computeControlTorques()
+    c.enableJointLimitAvoidance(False)
+    assert np.array_equal(a, c.computeControlTorques())
