@@ -276,6 +276,13 @@ int64_t osc_launch_count(const osc_handle* h);
  * For the link frame + point of motion-force task `task_id` (or, when task_id < 0, of `frame` and `point`):
  *   M (n*n, row-major), J (6*n row-major, linear rows first: SaiModel::JWorldFrame), x (3), R (9), g (n).
  * Any output pointer may be NULL. */
+/* ---- simulation side of the loop.  Replaces what the reference examples obtain from
+ * sai-simulation: sim->setJointTorques(name, tau); sim->integrate()
+ * (examples/05-using_robot_controller/05-using_robot_controller.cpp:223-231).  Forward dynamics
+ * ddq = M^-1 (tau - b(q, dq) - g(q)) of the handle's model for every robot, `substeps` semi-implicit Euler steps of
+ * `dt` with the torque held; q and dq (n x N, SoA) are updated in place, host or device memory. ---- */
+int osc_sim_integrate(osc_handle* h, double* q, double* dq, const double* tau, double dt, int substeps, int mem_kind);
+
 int osc_eval_model(osc_handle* h, int task_id, const osc_link_frame* frame, const double point[3], double* M,
 				   double* J, double* x, double* R, double* g, int mem_kind);
 

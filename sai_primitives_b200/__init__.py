@@ -8,6 +8,7 @@ from .batched import (  # noqa: F401
     FULL_DYNAMIC_DECOUPLING,
     IMPEDANCE,
     BatchedRobot,
+    BatchedSimulation,
     JointTask,
     MotionForceTask,
     RobotController,

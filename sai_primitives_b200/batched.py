@@ -144,6 +144,40 @@ class BatchedRobot:
         _check(self.handle, self._lib.osc_set_stream(self.handle, C.c_void_p(cuda_stream_ptr)))
 
 
+class BatchedSimulation:
+    """Simulation side of the control loop for N robots, with the method names the reference examples
+    use on sai-simulation (examples/05-using_robot_controller/05-using_robot_controller.cpp:223-231): setTimestep,
+    setJointTorques, integrate, getJointPositions, getJointVelocities.  Semi-implicit Euler on
+    ddq = M^-1 (tau - b - g) of the robot's model; state and torques are robots x dof arrays."""
+
+    def __init__(self, robot: BatchedRobot, q, dq, timestep=0.001):
+        self._robot = robot
+        self._lib = robot._lib
+        n, N = robot.dof(), robot.n_robots
+        self._q = np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(N, n).T)
+        self._dq = np.ascontiguousarray(np.asarray(dq, dtype=np.float64).reshape(N, n).T)
+        self._tau = np.zeros((n, N))
+        self._dt = float(timestep)
+
+    def setTimestep(self, dt):
+        self._dt = float(dt)
+
+    def setJointTorques(self, tau):
+        n, N = self._robot.dof(), self._robot.n_robots
+        self._tau = np.ascontiguousarray(np.asarray(tau, dtype=np.float64).reshape(N, n).T)
+
+    def integrate(self, substeps=1):
+        P = C.POINTER(C.c_double)
+        _check(self._robot.handle, self._lib.osc_sim_integrate(self._robot.handle, self._q.ctypes.data_as(P), self._dq.ctypes.data_as(P),
+                                                               self._tau.ctypes.data_as(P), self._dt, int(substeps), capi.OSC_MEM_HOST))
+
+    def getJointPositions(self):
+        return self._q.T.copy()
+
+    def getJointVelocities(self):
+        return self._dq.T.copy()
+
+
 class _Task:
     def __init__(self, robot: BatchedRobot, task_name, loop_timestep):
         self._robot = robot

@@ -22,6 +22,10 @@ cudaError_t launch_reinit_mft(const OscProgram& P, int mft_index, int full_init,
 	DISPATCH_N(P.model.n, (reinit_mft_kernel<N_><<<grid_for(P.n_robots, 128), 128, 0, stream>>>(P, mft_index, full_init)));
 	return cudaGetLastError();
 }
+cudaError_t launch_sim_integrate(const OscProgram& P, double* q, double* dq, const double* tau, double dt, int substeps, cudaStream_t stream) {
+	DISPATCH_N(P.model.n, (sim_integrate_kernel<N_><<<grid_for(P.n_robots, 128), 128, 0, stream>>>(P, q, dq, tau, dt, substeps)));
+	return cudaGetLastError();
+}
 cudaError_t launch_jla(const OscProgram& P, cudaStream_t stream) {
 	DevJla jp;	// JointLimitAvoidanceTask.h:26-35
 	jp.kv = 20.0;

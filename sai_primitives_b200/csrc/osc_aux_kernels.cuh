@@ -347,5 +347,45 @@ __global__ void __launch_bounds__(128) jla_kernel(const __grid_constant__ OscPro
 	for (int j = 0; j < N; j++) P.tau[(int64_t)j * NR + i] = tau[j];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Simulation side of the loop: ddq = M^-1 (tau - b - g), semi-implicit Euler, `substeps` steps of dt
+// with the torque held.  q and dq are updated in place.
+template <int N>
+__global__ void __launch_bounds__(128) sim_integrate_kernel(const __grid_constant__ OscProgram P, double* qio, double* dqio, const double* tau_in,
+															 double dt, int substeps) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t NR = P.n_robots;
+	if (i >= NR) return;
+	double q[N], dq[N], tau[N];
+#pragma unroll
+	for (int j = 0; j < N; j++) {
+		q[j] = qio[(int64_t)j * NR + i];
+		dq[j] = dqio[(int64_t)j * NR + i];
+		tau[j] = tau_in[(int64_t)j * NR + i];
+	}
+	for (int s = 0; s < substeps; s++) {
+		KinDyn<N> kd;
+		forward_kinematics<N>(P.model, q, kd);
+		mass_matrix<N, false>(P.model, kd);
+		double rhs[N];
+		rnea_bias<N>(P.model, kd, dq, rhs);
+		double invd[N];
+#pragma unroll
+		for (int j = 0; j < N; j++) rhs[j] = tau[j] - rhs[j];
+		cholesky_lower<N>(kd.M, invd);
+		solve_spd<N>(kd.M, invd, rhs);
+#pragma unroll
+		for (int j = 0; j < N; j++) {
+			dq[j] += rhs[j] * dt;
+			q[j] += dq[j] * dt;
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < N; j++) {
+		qio[(int64_t)j * NR + i] = q[j];
+		dqio[(int64_t)j * NR + i] = dq[j];
+	}
+}
+
 #undef ST
 }  // namespace osc

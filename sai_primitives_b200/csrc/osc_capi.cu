@@ -1038,6 +1038,28 @@ static int step_impl(osc_handle* h, const double* q, const double* dq, double* t
 	return run_cycle(h, tau_out, mem_kind, sync_host);
 }
 
+int osc_sim_integrate(osc_handle* h, double* q, double* dq, const double* tau, double dt, int substeps, int mem_kind) {
+	ENTER(h);
+	if (!q || !dq || !tau) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null pointer");
+	if (!(dt > 0.0) || substeps < 1) return fail(h, OSC_ERR_INVALID_ARGUMENT, "timestep must be positive and substeps >= 1");
+	const size_t bytes = (size_t)h->model.n * h->NR * sizeof(double);
+	if (mem_kind == OSC_MEM_DEVICE) {
+		CUDA_TRY(h, osc::launch_sim_integrate(h->prog, q, dq, tau, dt, substeps, h->stream));
+	} else if (mem_kind == OSC_MEM_HOST) {
+		CUDA_TRY(h, cudaMemcpyAsync(h->d_q, q, bytes, cudaMemcpyHostToDevice, h->stream));
+		CUDA_TRY(h, cudaMemcpyAsync(h->d_dq, dq, bytes, cudaMemcpyHostToDevice, h->stream));
+		CUDA_TRY(h, cudaMemcpyAsync(h->d_tau, tau, bytes, cudaMemcpyHostToDevice, h->stream));
+		CUDA_TRY(h, osc::launch_sim_integrate(h->prog, h->d_q, h->d_dq, h->d_tau, dt, substeps, h->stream));
+		CUDA_TRY(h, cudaMemcpyAsync(q, h->d_q, bytes, cudaMemcpyDeviceToHost, h->stream));
+		CUDA_TRY(h, cudaMemcpyAsync(dq, h->d_dq, bytes, cudaMemcpyDeviceToHost, h->stream));
+		CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+	} else {
+		return fail(h, OSC_ERR_INVALID_ARGUMENT, "bad mem_kind");
+	}
+	h->launches += 1;
+	return OSC_OK;
+}
+
 int osc_get_status(osc_handle* h, uint32_t* flags_out, int mem_kind) {
 	ENTER(h);
 	if (!flags_out) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null output");

@@ -198,6 +198,90 @@ DEVI void mass_matrix(const DevModel& m, KinDyn<N>& kd) {
 	}
 }
 
+// Bias forces b(q, dq) + g(q) by the recursive Newton-Euler algorithm in world coordinates (the
+// simulation side of the loop; restated in oracle/simulation.py).  The base is at rest and "accelerates" with -gravity.
+template <int N>
+DEVI void rnea_bias(const DevModel& m, const KinDyn<N>& kd, const double (&dq)[N], double (&tau)[N]) {
+	double W[N][3], AL[N][3], AP[N][3];
+	double w[3] = {0, 0, 0}, al[3] = {0, 0, 0}, ap[3] = {-m.gravity[0], -m.gravity[1], -m.gravity[2]};
+	double pp[3] = {0, 0, 0};
+#pragma unroll
+	for (int k = 0; k < N; k++) {
+		const double r[3] = {kd.p[k][0] - pp[0], kd.p[k][1] - pp[1], kd.p[k][2] - pp[2]};
+		double t1[3], t2[3];
+		cross3(al, r, t1);
+		cross3(w, r, t2);
+		double t3[3];
+		cross3(w, t2, t3);
+#pragma unroll
+		for (int c = 0; c < 3; c++) ap[c] += t1[c] + t3[c];
+		cross3(w, kd.a[k], t1);
+		if (m.jtype[k] == 0) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				al[c] += t1[c] * dq[k];
+				w[c] += kd.a[k][c] * dq[k];
+			}
+		} else {
+#pragma unroll
+			for (int c = 0; c < 3; c++) ap[c] += 2.0 * t1[c] * dq[k];
+		}
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			W[k][c] = w[c];
+			AL[k][c] = al[c];
+			AP[k][c] = ap[c];
+			pp[c] = kd.p[k][c];
+		}
+	}
+	double f[3] = {0, 0, 0}, nm[3] = {0, 0, 0};
+#pragma unroll
+	for (int k = N - 1; k >= 0; k--) {
+		const double* R = kd.Rb[k];
+		double cw[3];
+		mat3_vec(R, m.com[k], cw);
+		// I_w x = R (I (R^T x))
+		auto apply_inertia = [&](const double x[3], double y[3]) {
+			double l[3], il[3];
+			mat3t_vec(R, x, l);
+			const double* Ib = m.inertia[k];
+			il[0] = Ib[0] * l[0] + Ib[1] * l[1] + Ib[2] * l[2];
+			il[1] = Ib[1] * l[0] + Ib[3] * l[1] + Ib[4] * l[2];
+			il[2] = Ib[2] * l[0] + Ib[4] * l[1] + Ib[5] * l[2];
+			mat3_vec(R, il, y);
+		};
+		double t1[3], t2[3], ac[3], F[3], Nc[3], Iw_w[3], Iw_al[3];
+		cross3(AL[k], cw, t1);
+		cross3(W[k], cw, t2);
+		double t3[3];
+		cross3(W[k], t2, t3);
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			ac[c] = AP[k][c] + t1[c] + t3[c];
+			F[c] = m.mass[k] * ac[c];
+		}
+		apply_inertia(W[k], Iw_w);
+		apply_inertia(AL[k], Iw_al);
+		cross3(W[k], Iw_w, t1);
+#pragma unroll
+		for (int c = 0; c < 3; c++) Nc[c] = Iw_al[c] + t1[c];
+		if (k < N - 1) {
+			const double d[3] = {kd.p[k + 1 < N ? k + 1 : k][0] - kd.p[k][0], kd.p[k + 1 < N ? k + 1 : k][1] - kd.p[k][1],
+								 kd.p[k + 1 < N ? k + 1 : k][2] - kd.p[k][2]};
+			cross3(d, f, t2);
+#pragma unroll
+			for (int c = 0; c < 3; c++) nm[c] += t2[c];
+		}
+		cross3(cw, F, t2);
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			nm[c] += Nc[c] + t2[c];
+			f[c] += F[c];
+		}
+		tau[k] = (m.jtype[k] == 0) ? dot3(kd.a[k], nm) : dot3(kd.a[k], f);
+	}
+}
+
 // 6 x n world-frame Jacobian (linear rows first) of point x fixed to body `body`,
 // stored transposed: JT[i][0..2] = linear column of joint i, JT[i][3..5] = angular.
 template <int N>

@@ -154,3 +154,43 @@ def test_joint_limit_avoidance_oracle_properties():
     a = c.computeControlTorques()
     c.enableJointLimitAvoidance(False)
     assert np.array_equal(a, c.computeControlTorques())
+
+
+@pytest.mark.parametrize("robot_name", ["panda", "panda_sliding_base", "rrrr"])
+def test_bias_forces_against_independent_statements(robot_name):
+    """oracle/simulation.py: recursive Newton-Euler bias forces vs (a) the gravity vector from the
+    Jacobians, (b) Coriolis/centrifugal forces from the Christoffel symbols of a finite-difference dM/dq, (c) the power
+    balance d/dt(1/2 dq^T M dq) = dq^T (tau - g) along an integrated trajectory."""
+    from oracle import simulation as SIM
+    from oracle.robots import make_chain
+    from oracle.sai_model import SaiModel
+    ch = make_chain(robot_name)
+    rng = np.random.default_rng(7)
+    m = SaiModel(ch)
+    q = ch.q_lower + rng.random(ch.n) * (ch.q_upper - ch.q_lower)
+    dq = rng.uniform(-1, 1, ch.n)
+    m.setQ(q); m.setDq(np.zeros(ch.n)); m.updateModel()
+    assert np.allclose(SIM.bias_forces(m), m.jointGravityVector(), atol=1e-11)
+    m.setDq(dq); m.updateModel()
+    b = SIM.bias_forces(m) - m.jointGravityVector()
+    h = 1e-6
+    dM = np.zeros((ch.n, ch.n, ch.n))
+    for k in range(ch.n):
+        e = np.zeros(ch.n); e[k] = h
+        m.setQ(q + e); m.updateModel(); Mp = m.M()
+        m.setQ(q - e); m.updateModel(); Mm = m.M()
+        dM[:, :, k] = (Mp - Mm) / (2 * h)
+    m.setQ(q); m.updateModel()
+    c_ref = np.einsum("ijk,j,k->i", dM, dq, dq) - 0.5 * np.einsum("jki,j,k->i", dM, dq, dq)
+    assert np.abs(b - c_ref).max() < 1e-6 * max(1.0, np.abs(c_ref).max())
+    # power balance over a short trajectory with a constant torque
+    tau = rng.uniform(-2, 2, ch.n)
+    e0 = 0.5 * m.dq() @ m.M() @ m.dq()
+    work = 0.0
+    dt = 1e-5
+    for _ in range(200):
+        dq0 = m.dq(); g = m.jointGravityVector()
+        SIM.integrate(m, tau, dt)
+        work += 0.5 * (dq0 + m.dq()) @ (tau - g) * dt
+    e1 = 0.5 * m.dq() @ m.M() @ m.dq()
+    assert abs((e1 - e0) - work) < 2e-4 * max(1.0, abs(work))
