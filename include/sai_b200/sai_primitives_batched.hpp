@@ -434,4 +434,29 @@ private:
 	std::vector<std::string> _task_names;
 };
 
+// Simulation side of the loop for N robots with the method names the reference examples use on
+// sai-simulation (examples/05-using_robot_controller/05-using_robot_controller.cpp:223-231).  q, dq and tau are
+// caller-owned SoA arrays (dof x N), host or device; integrate() advances q and dq in place.
+class BatchedSimulation {
+public:
+	BatchedSimulation(std::shared_ptr<BatchedRobot>& robot, double* q, double* dq, osc_mem_kind where = OSC_MEM_HOST)
+		: _robot(robot), _q(q), _dq(dq), _where(where) {}
+	void setTimestep(double dt) { _dt = dt; }
+	void setJointTorques(const double* tau) { _tau = tau; }
+	void integrate(int substeps = 1) {
+		if (!_tau) throw std::invalid_argument("BatchedSimulation::integrate: no joint torques set");
+		check(_robot->handle(), osc_sim_integrate(_robot->handle(), _q, _dq, _tau, _dt, substeps, _where));
+	}
+	const double* getJointPositions() const { return _q; }
+	const double* getJointVelocities() const { return _dq; }
+
+private:
+	std::shared_ptr<BatchedRobot> _robot;
+	double* _q;
+	double* _dq;
+	const double* _tau = nullptr;
+	double _dt = 0.001;
+	osc_mem_kind _where;
+};
+
 }  // namespace SaiPrimitivesB200
