@@ -523,10 +523,13 @@ DEVI void forward_kinematics_rolled(const DevModel& m, const double (&qr)[N], do
 	double p[3] = {0, 0, 0};
 #pragma unroll
 	for (int i = 0; i < N; i++) smt[(size_t)(9 * i) * sms] = qr[i];
+	// sine and cosine of joint i + 1 are evaluated while the orientation of body i goes through its dependent chain
+	double sn, cn;
+	sincos_joint(qr[0], &sn, &cn);
 #pragma unroll 1
 	for (int i = 0; i < N; i++) {
-		double s, c;
-		sincos_joint(smt[(size_t)(9 * i) * sms], &s, &c);
+		const double s = sn, c = cn;
+		if (i + 1 < N) sincos_joint(smt[(size_t)(9 * (i + 1)) * sms], &sn, &cn);
 		double t[3];
 		mat3_vec(R, m.t_fix[i], t);
 		p[0] += t[0];
@@ -577,20 +580,30 @@ DEVI void mass_matrix_rolled(const DevModel& m, double* smt, int sms) {
 		const double ai[3] = {ap[0], ap[1 * sms], ap[2 * sms]};
 		const double pi[3] = {ap[3 * sms], ap[4 * sms], ap[5 * sms]};
 		const double* Ib = m.inertia[i];
-		double T[9];  // T = R * I
-#pragma unroll
-		for (int r = 0; r < 3; r++) {
-			T[3 * r + 0] = R[3 * r] * Ib[0] + R[3 * r + 1] * Ib[1] + R[3 * r + 2] * Ib[2];
-			T[3 * r + 1] = R[3 * r] * Ib[1] + R[3 * r + 1] * Ib[3] + R[3 * r + 2] * Ib[4];
-			T[3 * r + 2] = R[3 * r] * Ib[2] + R[3 * r + 1] * Ib[4] + R[3 * r + 2] * Ib[5];
-		}
+		const bool iso = (Ib[1] == 0.0) && (Ib[2] == 0.0) && (Ib[4] == 0.0) && (Ib[0] == Ib[3]) && (Ib[0] == Ib[5]);
 		double Iw[6];
-		Iw[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2];
-		Iw[1] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5];
-		Iw[2] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8];
-		Iw[3] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5];
-		Iw[4] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8];
-		Iw[5] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8];
+		if (iso) {	// R (k I) R^T = k I  (warp-uniform: a model constant)
+			Iw[0] = Ib[0];
+			Iw[1] = 0.0;
+			Iw[2] = 0.0;
+			Iw[3] = Ib[0];
+			Iw[4] = 0.0;
+			Iw[5] = Ib[0];
+		} else {
+			double T[9];  // T = R * I
+#pragma unroll
+			for (int r = 0; r < 3; r++) {
+				T[3 * r + 0] = R[3 * r] * Ib[0] + R[3 * r + 1] * Ib[1] + R[3 * r + 2] * Ib[2];
+				T[3 * r + 1] = R[3 * r] * Ib[1] + R[3 * r + 1] * Ib[3] + R[3 * r + 2] * Ib[4];
+				T[3 * r + 2] = R[3 * r] * Ib[2] + R[3 * r + 1] * Ib[4] + R[3 * r + 2] * Ib[5];
+			}
+			Iw[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2];
+			Iw[1] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5];
+			Iw[2] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8];
+			Iw[3] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5];
+			Iw[4] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8];
+			Iw[5] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8];
+		}
 		double c[3];
 		mat3_vec(R, m.com[i], c);
 		c[0] += pi[0];
@@ -619,13 +632,15 @@ DEVI void mass_matrix_rolled(const DevModel& m, double* smt, int sms) {
 		no[0] = cI[0] * ai[0] + cI[1] * ai[1] + cI[2] * ai[2] + t1[0];
 		no[1] = cI[1] * ai[0] + cI[3] * ai[1] + cI[4] * ai[2] + t1[1];
 		no[2] = cI[2] * ai[0] + cI[4] * ai[1] + cI[5] * ai[2] + t1[2];
-		// M(i, j) = a_j . (n_o + f x p_j); evaluated for every j (the entries above the diagonal are never read) so that
-		// the register indices stay compile-time constants
+		// M(i, j) = a_j . (n_o + f x p_j) for j <= i: the loop over j is unrolled (compile-time register indices) and the
+		// entries above the diagonal are skipped by a warp-uniform test
 #pragma unroll
 		for (int j = 0; j < N; j++) {
-			double fxp[3];
-			cross3(f, p[j], fxp);
-			Rs[j * sms] = a[j][0] * (no[0] + fxp[0]) + a[j][1] * (no[1] + fxp[1]) + a[j][2] * (no[2] + fxp[2]);
+			if (j <= i) {
+				double fxp[3];
+				cross3(f, p[j], fxp);
+				Rs[j * sms] = a[j][0] * (no[0] + fxp[0]) + a[j][1] * (no[1] + fxp[1]) + a[j][2] * (no[2] + fxp[2]);
+			}
 		}
 	}
 }

@@ -103,6 +103,36 @@ def test_config2_panda_osc_with_nullspace_joint_task(dec, use_prev):
     assert rel_err(tau, ref).max() < REL_TOL
 
 
+@pytest.mark.parametrize("N", [1, 31, 333])
+def test_config2_ragged_batch_sizes_multi_cycle(N):
+    """batch sizes that are not a multiple of the warp / block size (and odd, so that the component rows of the SoA state
+    are only 8-byte aligned), several cycles with integral gains so that the integrators the specialised kernel stages
+    through shared memory carry over"""
+    import sai_primitives_b200 as sp
+    q, dq, _ = sample_states("panda", N, min_sigma_ratio=0.09)
+    robot = sp.BatchedRobot("panda", N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    link, pt = TASK_POINTS["panda"]
+    mft = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt)))
+    jt = sp.JointTask(robot)
+    mft.setPosControlGains(100.0, 20.0, 35.0); mft.setOriControlGains(200.0, 28.3, 25.0); jt.setGains(50.0, 14.0, 12.0)
+    ctrl = sp.RobotController(robot, [mft, jt])
+    ob = OracleBatch("panda", N); ob.set_state(q, dq)
+    omft = ob.add_mft(link, (np.eye(3), np.array(pt))); ojt = ob.add_jt()
+    for a, b in zip(omft, ojt):
+        a.setPosControlGains(100.0, 20.0, 35.0); a.setOriControlGains(200.0, 28.3, 25.0); b.setGains(50.0, 14.0, 12.0)
+    ob.finalize()
+    _set_mft_goals(mft, omft, N); _set_joint_goals(jt, ojt, q, 7)
+    for cycle in range(4):
+        ctrl.updateControllerTaskModels()
+        tau = ctrl.computeControlTorques()
+        ref = ob.cycle()
+        assert (robot.status() & sp.capi.STATUS_UNHANDLED).sum() == 0
+        assert rel_err(tau, ref).max() < REL_TOL, cycle
+        q = q + 0.001 * dq
+        robot.setQ(q); robot.updateModel(); ob.set_state(q, dq)
+
+
 def test_config2_gravity_and_saturation():
     import sai_primitives_b200 as sp
     N = 64
