@@ -48,6 +48,14 @@ inline void check(osc_handle* h, int rc) {
 }
 
 // The SaiModel of the batch: N copies of one robot on one CUDA device.
+// the counterpart of `std::make_shared<SaiModel::SaiModel>(robot_file)`
+// (examples/05-using_robot_controller/05-using_robot_controller.cpp:64): registers a URDF serial chain under a name that
+// BatchedRobot(name, n) and the link-name arguments of the tasks then accept.
+inline void registerUrdfFile(const std::string& model_name, const std::string& urdf_file) {
+	if (osc_urdf_register_file(model_name.c_str(), urdf_file.c_str()) != OSC_OK)
+		throw std::invalid_argument("URDF [" + urdf_file + "]: " + osc_urdf_last_error());
+}
+
 class BatchedRobot {
 public:
 	BatchedRobot(const std::string& builtin_robot, int64_t n_robots, int device = 0) : _name(builtin_robot) {

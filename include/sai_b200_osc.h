@@ -183,6 +183,15 @@ const char* osc_last_error(const osc_handle* h);
 int osc_builtin_model(const char* robot_name, osc_model_desc* out);
 int osc_builtin_link(const char* robot_name, const char* link_name, osc_link_frame* out);
 
+/* ---- URDF models.  Replaces std::make_shared<SaiModel::SaiModel>(robot_file)
+ * (examples/05-using_robot_controller/05-using_robot_controller.cpp:64) for serial chains: links attached through
+ * fixed joints are merged into their parent body, the root link is welded to the world.  The model is registered
+ * under `model_name` and then served by osc_builtin_model / osc_builtin_link like the built-in ones (set
+ * R_world_base / t_world_base of the description for SaiModel::setTRobotBase). ---- */
+int osc_urdf_register(const char* model_name, const char* urdf_xml);
+int osc_urdf_register_file(const char* model_name, const char* path);
+const char* osc_urdf_last_error(void);
+
 /* ---- lifetime.  Replaces make_shared<SaiModel>(urdf) + task/controller construction ---- */
 int osc_create(const osc_model_desc* model, int64_t n_robots, int device, osc_handle** out);
 int osc_destroy(osc_handle* h);

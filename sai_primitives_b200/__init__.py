@@ -12,4 +12,5 @@ from .batched import (  # noqa: F401
     JointTask,
     MotionForceTask,
     RobotController,
+    registerUrdf,
 )

@@ -45,6 +45,20 @@ def _soa(a, n_robots, ncomp):
     raise ValueError("expected an array of shape (%d, %d), got %s" % (n_robots, ncomp, a.shape))
 
 
+def registerUrdf(model_name, urdf_file_or_text):
+    """make a URDF robot (a serial chain) available under `model_name`, the counterpart of
+    `SaiModel(robot_file)` (examples/05-using_robot_controller/05-using_robot_controller.cpp:64).  Accepts a file name
+    or the XML text; afterwards `BatchedRobot(model_name, n_robots)` and link names work as for the built-in robots."""
+    lib = capi.load_library()
+    text = str(urdf_file_or_text)
+    if text.lstrip().startswith("<"):
+        rc = lib.osc_urdf_register(model_name.encode(), text.encode())
+    else:
+        rc = lib.osc_urdf_register_file(model_name.encode(), text.encode())
+    if rc != 0:
+        raise ValueError("URDF [%s]: %s" % (model_name, lib.osc_urdf_last_error().decode()))
+
+
 class BatchedRobot:
     """N independent copies of one robot model on one CUDA device (the SaiModel of the batch)."""
 

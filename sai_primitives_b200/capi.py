@@ -175,6 +175,9 @@ SYMBOLS = {
     "osc_step_async": (C.c_int, [_H, _PD, _PD, _PD, C.c_int]),
     "osc_get_status": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "osc_launch_count": (C.c_int64, [_H]),
+    "osc_urdf_register": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "osc_urdf_register_file": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "osc_urdf_last_error": (C.c_char_p, []),
     "osc_sim_integrate": (C.c_int, [_H, _PD, _PD, _PD, C.c_double, C.c_int, C.c_int]),
     "osc_eval_model": (C.c_int, [_H, C.c_int, C.POINTER(LinkFrame), C.POINTER(D), _PD, _PD, _PD, _PD, _PD, C.c_int]),
 }

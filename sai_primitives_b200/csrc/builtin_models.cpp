@@ -8,7 +8,10 @@
 //   panda_sliding_base  examples/06-partial_joint_task/panda_arm_sliding_base.urdf:171-233
 //   rrrr                examples/11-planar_robot_controller/rrrrbot.urdf:5-166
 //   puma_like           authored here (the reference's puma.urdf lives in sai-model)
+#include <cctype>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -66,6 +69,8 @@ struct Link {
 	double mass;
 	V3 com;
 	V3 inertia_diag;
+	V3 inertia_off{0, 0, 0};  // ixy, ixz, iyz (URDF loader; the built-in tables are diagonal)
+	V3 com_rpy{0, 0, 0};	  // orientation of the inertial frame in the link frame
 };
 
 struct Built {
@@ -143,8 +148,10 @@ Built build(const std::vector<Link>& links) {
 		b.frames[l.name] = f;
 		if (body >= 0) {
 			const V3 c = add(t_lb, mul(R_lb, l.com));
-			M3 Id{{l.inertia_diag.x, 0, 0, 0, l.inertia_diag.y, 0, 0, 0, l.inertia_diag.z}};
-			const M3 Ic = mul(mul(R_lb, Id), transpose(R_lb));
+			M3 Id{{l.inertia_diag.x, l.inertia_off.x, l.inertia_off.y, l.inertia_off.x, l.inertia_diag.y, l.inertia_off.z, l.inertia_off.y,
+				   l.inertia_off.z, l.inertia_diag.z}};
+			const M3 R_li = mul(R_lb, rpy(l.com_rpy.x, l.com_rpy.y, l.com_rpy.z));	 // inertial frame in the body frame
+			const M3 Ic = mul(mul(R_li, Id), transpose(R_li));
 			am += l.mass;
 			ah = add(ah, V3{l.mass * c.x, l.mass * c.y, l.mass * c.z});
 			add_second_moment(aI, Ic, l.mass, c);
@@ -203,7 +210,16 @@ std::vector<Link> puma_links() {
 	};
 }
 
+std::map<std::string, Built>& registered() {
+	static std::map<std::string, Built> m;
+	return m;
+}
+
 const Built* lookup(const char* name) {
+	if (name) {
+		auto r = registered().find(name);
+		if (r != registered().end()) return &r->second;
+	}
 	static const std::map<std::string, Built> models = [] {
 		std::map<std::string, Built> m;
 		m["panda"] = build(panda_links());
@@ -217,7 +233,316 @@ const Built* lookup(const char* name) {
 	return it == models.end() ? nullptr : &it->second;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// URDF -> model.  Replaces `std::make_shared<SaiModel::SaiModel>(robot_file)`
+// (examples/05-using_robot_controller/05-using_robot_controller.cpp:64) for serial chains: the subset of URDF that
+// carries the dynamics (link/inertial, joint/parent/child/origin/axis/limit); visuals and collisions are skipped.
+struct XmlTag {
+	std::string name;
+	std::map<std::string, std::string> attr;
+	bool closing = false, self_closing = false;
+};
+
+// next tag at or after pos; comments, processing instructions and text are skipped
+bool next_tag(const std::string& x, size_t& pos, XmlTag& t) {
+	for (;;) {
+		const size_t lt = x.find('<', pos);
+		if (lt == std::string::npos) return false;
+		if (x.compare(lt, 4, "<!--") == 0) {
+			const size_t e = x.find("-->", lt + 4);
+			if (e == std::string::npos) return false;
+			pos = e + 3;
+			continue;
+		}
+		if (x.compare(lt, 2, "<?") == 0 || x.compare(lt, 2, "<!") == 0) {
+			const size_t e = x.find('>', lt);
+			if (e == std::string::npos) return false;
+			pos = e + 1;
+			continue;
+		}
+		size_t gt = lt + 1;
+		char quote = 0;
+		for (; gt < x.size(); gt++) {  // '>' inside a quoted value does not end the tag
+			const char c = x[gt];
+			if (quote) {
+				if (c == quote) quote = 0;
+			} else if (c == '"' || c == '\'') {
+				quote = c;
+			} else if (c == '>') {
+				break;
+			}
+		}
+		if (gt >= x.size()) return false;
+		std::string body = x.substr(lt + 1, gt - lt - 1);
+		pos = gt + 1;
+		t = XmlTag();
+		if (!body.empty() && body[0] == '/') {
+			t.closing = true;
+			body = body.substr(1);
+		}
+		if (!body.empty() && body.back() == '/') {
+			t.self_closing = true;
+			body.pop_back();
+		}
+		size_t i = 0;
+		auto skip_ws = [&] { while (i < body.size() && std::isspace((unsigned char)body[i])) i++; };
+		skip_ws();
+		const size_t n0 = i;
+		while (i < body.size() && !std::isspace((unsigned char)body[i])) i++;
+		t.name = body.substr(n0, i - n0);
+		for (;;) {
+			skip_ws();
+			if (i >= body.size()) break;
+			const size_t k0 = i;
+			while (i < body.size() && body[i] != '=' && !std::isspace((unsigned char)body[i])) i++;
+			const std::string key = body.substr(k0, i - k0);
+			skip_ws();
+			if (i >= body.size() || body[i] != '=') continue;
+			i++;
+			skip_ws();
+			if (i >= body.size() || (body[i] != '"' && body[i] != '\'')) break;
+			const char q = body[i++];
+			const size_t v0 = i;
+			while (i < body.size() && body[i] != q) i++;
+			t.attr[key] = body.substr(v0, i - v0);
+			if (i < body.size()) i++;
+		}
+		return true;
+	}
+}
+
+// "a b c" the way the URDF readers do it: strtod one number after the other (a malformed literal such as "0.-75"
+// yields 0, like atof)
+V3 parse_v3(const std::string& s, V3 def) {
+	double v[3] = {def.x, def.y, def.z};
+	const char* p = s.c_str();
+	for (int k = 0; k < 3; k++) {
+		char* e = nullptr;
+		const double d = std::strtod(p, &e);
+		if (e == p) break;
+		v[k] = d;
+		p = e;
+		while (*p && !std::isspace((unsigned char)*p)) p++;	 // drop the unparsed rest of a malformed token
+	}
+	return V3{v[0], v[1], v[2]};
+}
+double parse_d(const std::map<std::string, std::string>& a, const char* key, double def) {
+	auto it = a.find(key);
+	if (it == a.end()) return def;
+	char* e = nullptr;
+	const double d = std::strtod(it->second.c_str(), &e);
+	return e == it->second.c_str() ? def : d;
+}
+
+struct UrdfLink {
+	std::string name;
+	double mass = 0;
+	V3 com{0, 0, 0}, com_rpy{0, 0, 0}, idiag{0, 0, 0}, ioff{0, 0, 0};
+};
+struct UrdfJoint {
+	std::string name, type, parent, child;
+	V3 xyz{0, 0, 0}, rpy_{0, 0, 0}, axis{1, 0, 0};
+	double lower = 0, upper = 0, velocity = 0, effort = 0;
+	bool has_limit = false;
+};
+
+// returns an empty string on success, else the reason
+std::string urdf_to_built(const std::string& xml, Built& out, std::vector<std::string>& name_store) {
+	std::vector<UrdfLink> links;
+	std::vector<UrdfJoint> joints;
+	size_t pos = 0;
+	XmlTag t;
+	int in_link = -1, in_joint = -1;
+	bool in_inertial = false;
+	int skip_depth = 0;	 // inside <visual>/<collision>/<transmission>/...: ignore everything
+	std::string skip_name;
+	bool saw_robot = false;
+	while (next_tag(xml, pos, t)) {
+		if (skip_depth > 0) {
+			if (t.name == skip_name) {
+				if (t.closing) skip_depth--;
+				else if (!t.self_closing) skip_depth++;
+			}
+			continue;
+		}
+		if (t.name == "robot") {
+			saw_robot = true;
+			continue;
+		}
+		if (t.closing) {
+			if (t.name == "link") in_link = -1;
+			else if (t.name == "joint") in_joint = -1;
+			else if (t.name == "inertial") in_inertial = false;
+			continue;
+		}
+		if (in_link < 0 && in_joint < 0) {
+			if (t.name == "link") {
+				UrdfLink l;
+				l.name = t.attr["name"];
+				links.push_back(l);
+				if (!t.self_closing) in_link = (int)links.size() - 1;
+			} else if (t.name == "joint") {
+				UrdfJoint j;
+				j.name = t.attr["name"];
+				j.type = t.attr["type"];
+				joints.push_back(j);
+				if (!t.self_closing) in_joint = (int)joints.size() - 1;
+			} else if (!t.self_closing) {  // material, gazebo, transmission ... at robot level
+				skip_name = t.name;
+				skip_depth = 1;
+			}
+			continue;
+		}
+		if (in_link >= 0) {
+			UrdfLink& l = links[in_link];
+			if (t.name == "inertial") {
+				in_inertial = !t.self_closing;
+			} else if (in_inertial && t.name == "origin") {
+				l.com = parse_v3(t.attr["xyz"], V3{0, 0, 0});
+				l.com_rpy = parse_v3(t.attr["rpy"], V3{0, 0, 0});
+			} else if (in_inertial && t.name == "mass") {
+				l.mass = parse_d(t.attr, "value", 0.0);
+			} else if (in_inertial && t.name == "inertia") {
+				l.idiag = V3{parse_d(t.attr, "ixx", 0), parse_d(t.attr, "iyy", 0), parse_d(t.attr, "izz", 0)};
+				l.ioff = V3{parse_d(t.attr, "ixy", 0), parse_d(t.attr, "ixz", 0), parse_d(t.attr, "iyz", 0)};
+			} else if (!in_inertial && !t.self_closing) {  // visual, collision
+				skip_name = t.name;
+				skip_depth = 1;
+			}
+			continue;
+		}
+		UrdfJoint& j = joints[in_joint];
+		if (t.name == "parent") j.parent = t.attr["link"];
+		else if (t.name == "child") j.child = t.attr["link"];
+		else if (t.name == "origin") {
+			j.xyz = parse_v3(t.attr["xyz"], V3{0, 0, 0});
+			j.rpy_ = parse_v3(t.attr["rpy"], V3{0, 0, 0});
+		} else if (t.name == "axis") j.axis = parse_v3(t.attr["xyz"], V3{1, 0, 0});
+		else if (t.name == "limit") {
+			j.has_limit = true;
+			j.lower = parse_d(t.attr, "lower", 0);
+			j.upper = parse_d(t.attr, "upper", 0);
+			j.velocity = parse_d(t.attr, "velocity", 0);
+			j.effort = parse_d(t.attr, "effort", 0);
+		} else if (!t.self_closing) {
+			skip_name = t.name;
+			skip_depth = 1;
+		}
+	}
+	if (!saw_robot || links.empty()) return "no <robot> with links found";
+	// the chain: root = the link that is nobody's child; every link must have at most one child joint
+	std::map<std::string, int> link_index, child_joint_of, parent_joint_of;
+	for (size_t i = 0; i < links.size(); i++) link_index[links[i].name] = (int)i;
+	for (size_t k = 0; k < joints.size(); k++) {
+		const UrdfJoint& j = joints[k];
+		if (!link_index.count(j.parent) || !link_index.count(j.child)) return "joint [" + j.name + "] refers to an unknown link";
+		if (child_joint_of.count(j.parent)) return "link [" + j.parent + "] has several children: only serial chains are supported";
+		if (parent_joint_of.count(j.child)) return "link [" + j.child + "] has several parents";
+		child_joint_of[j.parent] = (int)k;
+		parent_joint_of[j.child] = (int)k;
+	}
+	std::string root;
+	for (const UrdfLink& l : links)
+		if (!parent_joint_of.count(l.name)) {
+			if (!root.empty()) return "several root links: only one serial chain is supported";
+			root = l.name;
+		}
+	if (root.empty()) return "no root link (kinematic loop)";
+	name_store.clear();
+	name_store.reserve(links.size());
+	std::vector<Link> chain;
+	std::string cur = root;
+	const UrdfJoint* via = nullptr;
+	int dof = 0;
+	for (size_t guard = 0; guard <= links.size(); guard++) {
+		const UrdfLink& ul = links[link_index[cur]];
+		name_store.push_back(ul.name);
+		Link l{};
+		l.name = nullptr;  // fixed up below (name_store may not reallocate: reserved)
+		l.jtype = FIXED;
+		l.xyz = V3{0, 0, 0};
+		l.rpy_ = V3{0, 0, 0};
+		l.axis = V3{0, 0, 1};
+		if (via) {
+			l.xyz = via->xyz;
+			l.rpy_ = via->rpy_;
+			if (via->type == "revolute" || via->type == "continuous" || via->type == "prismatic") {
+				l.jtype = via->type == "prismatic" ? PRISMATIC : REVOLUTE;
+				l.axis = via->axis;
+				const double big = 1.7976931348623157e308;
+				l.lower = (via->type == "continuous" || !via->has_limit) ? -big : via->lower;
+				l.upper = (via->type == "continuous" || !via->has_limit) ? big : via->upper;
+				l.velocity = via->has_limit ? via->velocity : big;
+				l.effort = via->has_limit ? via->effort : big;
+				dof++;
+			} else if (via->type != "fixed") {
+				return "joint [" + via->name + "] has unsupported type [" + via->type + "]";
+			}
+		}
+		l.mass = ul.mass;
+		l.com = ul.com;
+		l.inertia_diag = ul.idiag;
+		l.inertia_off = ul.ioff;
+		l.com_rpy = ul.com_rpy;
+		chain.push_back(l);
+		auto nx = child_joint_of.find(cur);
+		if (nx == child_joint_of.end()) break;
+		via = &joints[nx->second];
+		cur = via->child;
+	}
+	if (chain.size() != links.size()) return "links outside the chain";
+	if (dof < 1 || dof > OSC_MAX_DOF) return "the chain must have between 1 and OSC_MAX_DOF moving joints";
+	for (size_t i = 0; i < chain.size(); i++) chain[i].name = name_store[i].c_str();
+	out = build(chain);
+	return "";
+}
+
+std::string& urdf_error() {
+	static std::string e;
+	return e;
+}
+
 }  // namespace
+
+/* SURVEY.md row f-3 */
+extern "C" int osc_urdf_register(const char* model_name, const char* urdf_xml) {
+	if (!model_name || !urdf_xml || !*model_name) {
+		urdf_error() = "null argument";
+		return OSC_ERR_INVALID_ARGUMENT;
+	}
+	static std::map<std::string, std::vector<std::string>> names;	// keeps the link names of registered models alive
+	Built b;
+	std::vector<std::string> store;
+	const std::string why = urdf_to_built(urdf_xml, b, store);
+	if (!why.empty()) {
+		urdf_error() = why;
+		return OSC_ERR_INVALID_ARGUMENT;
+	}
+	names[model_name] = std::move(store);
+	registered()[model_name] = b;
+	urdf_error().clear();
+	return OSC_OK;
+}
+
+extern "C" int osc_urdf_register_file(const char* model_name, const char* path) {
+	if (!path) {
+		urdf_error() = "null path";
+		return OSC_ERR_INVALID_ARGUMENT;
+	}
+	FILE* f = std::fopen(path, "rb");
+	if (!f) {
+		urdf_error() = std::string("cannot open [") + path + "]";
+		return OSC_ERR_INVALID_ARGUMENT;
+	}
+	std::string xml;
+	char buf[65536];
+	size_t n;
+	while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) xml.append(buf, n);
+	std::fclose(f);
+	return osc_urdf_register(model_name, xml.c_str());
+}
+
+extern "C" const char* osc_urdf_last_error(void) { return urdf_error().c_str(); }
 
 extern "C" int osc_builtin_model(const char* robot_name, osc_model_desc* out) {
 	const Built* b = lookup(robot_name);
