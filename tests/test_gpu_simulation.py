@@ -58,3 +58,26 @@ def test_closed_loop_batch_reaches_the_goals():
     err = np.linalg.norm(mft.getCurrentPosition() - goal, axis=1)
     assert err.max() < 2e-3, err.max()
     assert np.abs(sim.getJointVelocities()).max() < 0.05
+
+
+def test_urdf_registered_robot_runs_like_the_builtin_one():
+    """SURVEY.md row f-3 on the GPU: a robot registered from URDF text drives the same kernels as the built-in table"""
+    import sai_primitives_b200 as sp
+    from oracle import robots as OR
+    from tests.test_urdf_loader import _urdf_text
+    N = 40
+    sp.registerUrdf("urdf_panda_gpu", _urdf_text(OR.DESCRIPTIONS["panda"]()))
+    q, dq, _ = sample_states("panda", N, min_sigma_ratio=0.09)
+    link, pt = TASK_POINTS["panda"]
+    taus = []
+    for name in ("panda", "urdf_panda_gpu"):
+        robot = sp.BatchedRobot(name, N)
+        robot.setQ(q); robot.setDq(dq); robot.updateModel()
+        mft = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt)))
+        jt = sp.JointTask(robot)
+        ctrl = sp.RobotController(robot, [mft, jt])
+        mft.setGoalPosition(mft.getCurrentPosition() + 0.02); jt.setGoalPosition(q + 0.1)
+        ctrl.updateControllerTaskModels()
+        taus.append(ctrl.computeControlTorques())
+        assert (robot.status() & sp.capi.STATUS_UNHANDLED).sum() == 0
+    assert np.abs(taus[0] - taus[1]).max() <= 1e-11 * np.abs(taus[0]).max()
