@@ -349,8 +349,10 @@ int osc_create(const osc_model_desc* model, int64_t n_robots, int device, osc_ha
 	h->stream = h->own_stream;
 	const size_t n = (size_t)model->n;
 	int rc;
-	if ((rc = dev_alloc(h, &h->d_q, n * n_robots, true)) != OSC_OK) return cleanup(rc);
-	if ((rc = dev_alloc(h, &h->d_dq, n * n_robots, true)) != OSC_OK) return cleanup(rc);
+	// q and dq staging buffers are one allocation, so that host state that is contiguous too ([q; dq]) crosses PCIe in
+	// a single copy (h2d_state below)
+	if ((rc = dev_alloc(h, &h->d_q, 2 * n * n_robots, true)) != OSC_OK) return cleanup(rc);
+	h->d_dq = h->d_q + n * n_robots;
 	if ((rc = dev_alloc(h, &h->d_tau, n * n_robots, true)) != OSC_OK) return cleanup(rc);
 	if ((rc = dev_alloc(h, &h->d_status, (size_t)n_robots, true)) != OSC_OK) return cleanup(rc);
 	h->prog.q = h->d_q;
@@ -393,13 +395,21 @@ int64_t osc_num_robots(const osc_handle* h) { return h ? h->NR : 0; }
 int osc_dof(const osc_handle* h) { return h ? h->model.n : 0; }
 int64_t osc_launch_count(const osc_handle* h) { return h ? h->launches : 0; }
 
+// host q, dq -> the handle's staging buffers: one copy when the caller's arrays are adjacent, else two
+static cudaError_t h2d_state(osc_handle* h, const double* q, const double* dq) {
+	const size_t count = (size_t)h->model.n * h->NR;
+	if (dq == q + count) return cudaMemcpyAsync(h->d_q, q, 2 * count * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+	cudaError_t e = cudaMemcpyAsync(h->d_q, q, count * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+	if (e != cudaSuccess) return e;
+	return cudaMemcpyAsync(h->d_dq, dq, count * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+}
+
 int osc_set_state(osc_handle* h, const double* q, const double* dq, int mem_kind) {
 	ENTER(h);
 	if (!q || !dq) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null state pointer");
 	const size_t bytes = (size_t)h->model.n * h->NR * sizeof(double);
 	if (mem_kind == OSC_MEM_HOST) {
-		CUDA_TRY(h, cudaMemcpyAsync(h->d_q, q, bytes, cudaMemcpyHostToDevice, h->stream));
-		CUDA_TRY(h, cudaMemcpyAsync(h->d_dq, dq, bytes, cudaMemcpyHostToDevice, h->stream));
+		CUDA_TRY(h, h2d_state(h, q, dq));
 		// the caller may reuse its (pageable) buffers as soon as we return
 		CUDA_TRY(h, cudaStreamSynchronize(h->stream));
 		h->prog.q = h->d_q;
@@ -1024,8 +1034,7 @@ static int step_impl(osc_handle* h, const double* q, const double* dq, double* t
 	if (!q || !dq) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null state pointer");
 	const size_t bytes = (size_t)h->model.n * h->NR * sizeof(double);
 	if (mem_kind == OSC_MEM_HOST) {
-		CUDA_TRY(h, cudaMemcpyAsync(h->d_q, q, bytes, cudaMemcpyHostToDevice, h->stream));
-		CUDA_TRY(h, cudaMemcpyAsync(h->d_dq, dq, bytes, cudaMemcpyHostToDevice, h->stream));
+		CUDA_TRY(h, h2d_state(h, q, dq));
 		h->prog.q = h->d_q;
 		h->prog.dq = h->d_dq;
 	} else if (mem_kind == OSC_MEM_DEVICE) {
@@ -1046,8 +1055,7 @@ int osc_sim_integrate(osc_handle* h, double* q, double* dq, const double* tau, d
 	if (mem_kind == OSC_MEM_DEVICE) {
 		CUDA_TRY(h, osc::launch_sim_integrate(h->prog, q, dq, tau, dt, substeps, h->stream));
 	} else if (mem_kind == OSC_MEM_HOST) {
-		CUDA_TRY(h, cudaMemcpyAsync(h->d_q, q, bytes, cudaMemcpyHostToDevice, h->stream));
-		CUDA_TRY(h, cudaMemcpyAsync(h->d_dq, dq, bytes, cudaMemcpyHostToDevice, h->stream));
+		CUDA_TRY(h, h2d_state(h, q, dq));
 		CUDA_TRY(h, cudaMemcpyAsync(h->d_tau, tau, bytes, cudaMemcpyHostToDevice, h->stream));
 		CUDA_TRY(h, osc::launch_sim_integrate(h->prog, h->d_q, h->d_dq, h->d_tau, dt, substeps, h->stream));
 		CUDA_TRY(h, cudaMemcpyAsync(q, h->d_q, bytes, cudaMemcpyDeviceToHost, h->stream));
