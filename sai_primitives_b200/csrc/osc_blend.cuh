@@ -44,9 +44,11 @@ DEVI void jacobi_eig6(double (&G)[6][6], double (&U)[6][6]) {
 			for (int q = p + 1; q < 6; q++) {
 				const double gpq = G[p][q];
 				if (fabs(gpq) > 1e-18 * (fabs(G[p][p]) + fabs(G[q][q]))) {
-					const double theta = (G[q][q] - G[p][p]) / (2.0 * gpq);
-					const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-					const double c = rsqrt(t * t + 1.0), s = t * c;
+					// lean reciprocal / square roots (osc_math.cuh): gpq is non-zero here and both radicands are >= 1; the
+					// library versions cost about a hundred instructions per rotation with their special-case branches
+					const double theta = (G[q][q] - G[p][p]) * (0.5 * rcp_nz(gpq));
+					const double t = (theta >= 0.0 ? 1.0 : -1.0) * rcp_nz(fabs(theta) + sqrt_pos(theta * theta + 1.0));
+					const double c = rsqrt_pos(t * t + 1.0), s = t * c;
 #pragma unroll
 					for (int k = 0; k < 6; k++) {  // G <- G J
 						const double gkp = G[k][p], gkq = G[k][q];
