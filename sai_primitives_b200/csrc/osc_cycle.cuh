@@ -170,12 +170,13 @@ DEVI void prefetch_block_rows(const OscProgram& P, uint64_t blk) {
 // element e of thread t at  sm[e * blockDim.x + t]  (conflict-free, 8-byte interleave).
 //
 // SPEC = true is the specialisation for the default configuration of the flagship hierarchy (cycle_spec_eligible()
-// in osc_launch.h states the conditions: every joint revolute about its local z axis, pure motion control, no velocity
-// saturation, no gravity compensation, FULL or BOUNDED_INERTIA decoupling).  Everything those conditions rule out is
+// in osc_cycle_kernels.cu states the conditions: every joint revolute about its local z axis, pure motion control, no
+// velocity saturation, FULL or BOUNDED_INERTIA decoupling).  Everything those conditions rule out is
 // compiled out, which brings the kernel from 223 KB to under 128 KB of code: beyond that size the instruction stream
 // no longer stays in the SM's instruction cache between blocks and every 256-byte line costs a round trip to L2
 // (profiles/r01_ifetch.md).  Robots whose bounded-inertia update has rank two or more leave through the general path.
-template <int N, int R, bool HAS_JT, bool FULL, bool SPEC = false>
+// GRAV (with SPEC only): gravity compensation compiled in; the non-specialised instantiations test the run-time flag.
+template <int N, int R, bool HAS_JT, bool FULL, bool SPEC = false, bool GRAV = false>
 __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(const __grid_constant__ OscProgram P) {
 	extern __shared__ double sm[];
 	// Programmatic dependent launch on both sides: the general-path kernel of this cycle may be scheduled into whatever
@@ -225,8 +226,9 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		forward_kinematics_s<N, false>(mdl, q, kd, smt, sms);
 
 	double tau[N];
+	double gvec_out[N];	 // gravity vector of the specialisation (GRAV), added after the saturation
 #pragma unroll
-	for (int j = 0; j < N; j++) tau[j] = 0.0;
+	for (int j = 0; j < N; j++) tau[j] = gvec_out[j] = 0.0;
 	uint32_t status = 0;
 
 	if constexpr (R == 0) {
@@ -276,7 +278,11 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		// are dead after this, the factor takes their place; only diag(M) is kept for the bounded-inertia variant.
 		double dqr[N];	// joint velocities for the Jacobian pass below, requested early
 		if constexpr (SPEC) {
-			mass_matrix_rolled<N>(mdl, smt, sms);
+			mass_matrix_rolled<N, GRAV>(mdl, smt, sms);
+			if constexpr (GRAV) {
+#pragma unroll
+				for (int j = 0; j < N; j++) gvec_out[j] = smt[(size_t)(9 * j + 8) * sms];
+			}
 #if defined(OSC_TRACE)
 			OSC_LS_K();
 #endif
@@ -719,6 +725,10 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			else if (tau[j] < -mdl.effort[j])
 				tau[j] = -mdl.effort[j];
 		}
+	}
+	if constexpr (SPEC && GRAV && R > 0) {
+#pragma unroll
+		for (int j = 0; j < N; j++) tau[j] += gvec_out[j];
 	}
 	if (!SPEC && P.gravity_comp) {
 #pragma unroll

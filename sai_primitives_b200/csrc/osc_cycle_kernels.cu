@@ -43,7 +43,7 @@ static bool cycle_spec_eligible(const OscProgram& P, bool has_jt) {
 	const DevModel& m = P.model;
 	for (int j = 0; j < m.n; j++)
 		if (m.jtype[j] != 0 || m.axis[j][0] != 0.0 || m.axis[j][1] != 0.0 || m.axis[j][2] != 1.0) return false;
-	if (P.gravity_comp || P.mft[0].body < 0) return false;
+	if (P.mft[0].body < 0) return false;
 	if ((unsigned long long)P.n_robots * (unsigned long long)MC_COUNT >= (1ull << 32)) return false;  // 32-bit element indices
 	// The specialisation carries the bounded-inertia update of rank <= 1 only (robots needing more are handed to the
 	// general path one by one, which is correct but slow): require that at most one diagonal entry of M can ever fall
@@ -72,7 +72,7 @@ static bool cycle_spec_eligible(const OscProgram& P, bool has_jt) {
 	return true;
 }
 
-template <int N, int R, bool JT, bool FULL, bool SPEC = false>
+template <int N, int R, bool JT, bool FULL, bool SPEC = false, bool GRAV = false>
 static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 	const unsigned grid = (unsigned)((P.n_robots + kCycleBlock - 1) / kCycleBlock);
 	constexpr int smem = cycle_smem_doubles<N, R, SPEC>() * kCycleBlock * (int)sizeof(double);
@@ -80,7 +80,7 @@ static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev < 0 || dev >= 64 || !configured[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(osc_cycle_kernel<N, R, JT, FULL, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaError_t e = cudaFuncSetAttribute(osc_cycle_kernel<N, R, JT, FULL, SPEC, GRAV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e != cudaSuccess) return e;
 		if (dev >= 0 && dev < 64) configured[dev] = true;
 	}
@@ -104,7 +104,7 @@ static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 		attr[0].val.programmaticStreamSerializationAllowed = 1;
 		cfg.attrs = attr;
 		cfg.numAttrs = 1;
-		cudaError_t e = cudaLaunchKernelEx(&cfg, osc_cycle_kernel<N, R, JT, FULL, SPEC>, P);
+		cudaError_t e = cudaLaunchKernelEx(&cfg, osc_cycle_kernel<N, R, JT, FULL, SPEC, GRAV>, P);
 		if (e != cudaSuccess) return e;
 	}
 #if defined(OSC_TRACE)
@@ -128,7 +128,9 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 	cudaError_t e0;
 	if constexpr (R == 6) {
 		if (P.mft[0].full)
-			e0 = cycle_spec_eligible(P, JT) ? launch_variant<N, R, JT, true, true>(P, stream) : launch_variant<N, R, JT, true>(P, stream);
+			e0 = !cycle_spec_eligible(P, JT) ? launch_variant<N, R, JT, true>(P, stream)
+				 : P.gravity_comp		   ? launch_variant<N, R, JT, true, true, true>(P, stream)
+										   : launch_variant<N, R, JT, true, true, false>(P, stream);
 		else
 			e0 = launch_variant<N, R, JT, false>(P, stream);
 	} else {

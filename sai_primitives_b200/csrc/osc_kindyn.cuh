@@ -557,8 +557,9 @@ DEVI void forward_kinematics_rolled(const DevModel& m, const double (&qr)[N], do
 	}
 }
 
-// composite-rigid-body mass matrix; on exit M(i, j), j <= i, is at slot 9 i + j
-template <int N>
+// composite-rigid-body mass matrix; on exit M(i, j), j <= i, is at slot 9 i + j and, WITH_GRAVITY, entry i of the
+// gravity vector at slot 9 i + 8
+template <int N, bool WITH_GRAVITY = false>
 DEVI void mass_matrix_rolled(const DevModel& m, double* smt, int sms) {
 	double a[N][3], p[N][3];
 #pragma unroll
@@ -632,6 +633,11 @@ DEVI void mass_matrix_rolled(const DevModel& m, double* smt, int sms) {
 		no[0] = cI[0] * ai[0] + cI[1] * ai[1] + cI[2] * ai[2] + t1[0];
 		no[1] = cI[1] * ai[0] + cI[3] * ai[1] + cI[4] * ai[2] + t1[1];
 		no[2] = cI[2] * ai[0] + cI[4] * ai[1] + cI[5] * ai[2] + t1[2];
+		if constexpr (WITH_GRAVITY) {	// -(s_i . gravity wrench of the composite about the origin)
+			double hg[3];
+			cross3(ch, m.gravity, hg);
+			Rs[8 * sms] = -(dot3(ai, hg) + cm * dot3(vo, m.gravity));
+		}
 		// M(i, j) = a_j . (n_o + f x p_j) for j <= i: the loop over j is unrolled (compile-time register indices) and the
 		// entries above the diagonal are skipped by a warp-uniform test
 #pragma unroll
