@@ -285,6 +285,10 @@ int64_t osc_launch_count(const osc_handle* h);
  * For the link frame + point of motion-force task `task_id` (or, when task_id < 0, of `frame` and `point`):
  *   M (n*n, row-major), J (6*n row-major, linear rows first: SaiModel::JWorldFrame), x (3), R (9), g (n).
  * Any output pointer may be NULL. */
+/* ---- measurement aid (no reference counterpart): sustained FP64 FMA rate of the device in TFLOP/s, from a DFMA-only
+ * kernel run for about `seconds` (bench.py reports the roofline against it next to the datasheet figure) ---- */
+int osc_measure_fp64_peak(osc_handle* h, double seconds, double* tflops_out);
+
 /* ---- simulation side of the loop.  Replaces what the reference examples obtain from
  * sai-simulation: sim->setJointTorques(name, tau); sim->integrate()
  * (examples/05-using_robot_controller/05-using_robot_controller.cpp:223-231).  Forward dynamics

@@ -22,6 +22,37 @@ cudaError_t launch_reinit_mft(const OscProgram& P, int mft_index, int full_init,
 	DISPATCH_N(P.model.n, (reinit_mft_kernel<N_><<<grid_for(P.n_robots, 128), 128, 0, stream>>>(P, mft_index, full_init)));
 	return cudaGetLastError();
 }
+cudaError_t measure_fp64_peak(double seconds, double* tflops, cudaStream_t stream) {
+	int dev = 0, sms = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	double* out = nullptr;
+	cudaError_t e = cudaMalloc(&out, sizeof(double));
+	if (e != cudaSuccess) return e;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	const int grid = sms * 2, block = 1024, iters = 2048;	// 2 x 32 warps per SM
+	const double flop_per_launch = 2.0 * 128.0 * iters * (double)grid * block;
+	double best = 0.0, spent = 0.0;
+	for (int rep = 0; rep < 10000 && spent < seconds; rep++) {
+		cudaEventRecord(e0, stream);
+		fp64_peak_kernel<<<grid, block, 0, stream>>>(out, 1.0000001, 1e-9, iters);
+		cudaEventRecord(e1, stream);
+		e = cudaEventSynchronize(e1);
+		if (e != cudaSuccess) break;
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		spent += ms * 1e-3;
+		const double t = flop_per_launch / (ms * 1e-3) / 1e12;
+		if (spent > 0.5 * seconds && t > best) best = t;	// the second half: clocks have settled under load
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(out);
+	*tflops = best;
+	return e == cudaSuccess ? cudaGetLastError() : e;
+}
 cudaError_t launch_sim_integrate(const OscProgram& P, double* q, double* dq, const double* tau, double dt, int substeps, cudaStream_t stream) {
 	DISPATCH_N(P.model.n, (sim_integrate_kernel<N_><<<grid_for(P.n_robots, 128), 128, 0, stream>>>(P, q, dq, tau, dt, substeps)));
 	return cudaGetLastError();

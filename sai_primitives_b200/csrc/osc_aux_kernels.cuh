@@ -387,5 +387,25 @@ __global__ void __launch_bounds__(128) sim_integrate_kernel(const __grid_constan
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP64 FMA issue-rate probe for the roofline denominator (SURVEY.md 8d asks for a measured FP64 figure next to the
+// datasheet one): eight independent DFMA chains per thread in a rolled loop, every SM full.
+__global__ void __launch_bounds__(1024) fp64_peak_kernel(double* out, double a, double b, int iters) {
+	double x[8];
+#pragma unroll
+	for (int c = 0; c < 8; c++) x[c] = 1e-3 * threadIdx.x + c;
+#pragma unroll 1
+	for (int it = 0; it < iters; it++) {
+#pragma unroll
+		for (int r = 0; r < 16; r++)
+#pragma unroll
+			for (int c = 0; c < 8; c++) x[c] = fma(x[c], a, b);
+	}
+	double s = 0.0;
+#pragma unroll
+	for (int c = 0; c < 8; c++) s += x[c];
+	if (s == 12345.678) out[0] = s;	 // never true: keeps the chains alive
+}
+
 #undef ST
 }  // namespace osc

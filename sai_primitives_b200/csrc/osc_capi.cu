@@ -1047,6 +1047,14 @@ static int step_impl(osc_handle* h, const double* q, const double* dq, double* t
 	return run_cycle(h, tau_out, mem_kind, sync_host);
 }
 
+int osc_measure_fp64_peak(osc_handle* h, double seconds, double* tflops_out) {
+	ENTER(h);
+	if (!tflops_out || !(seconds > 0.0)) return fail(h, OSC_ERR_INVALID_ARGUMENT, "bad argument");
+	CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+	CUDA_TRY(h, osc::measure_fp64_peak(seconds, tflops_out, h->stream));
+	return OSC_OK;
+}
+
 int osc_sim_integrate(osc_handle* h, double* q, double* dq, const double* tau, double dt, int substeps, int mem_kind) {
 	ENTER(h);
 	if (!q || !dq || !tau) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null pointer");
