@@ -46,7 +46,7 @@ def log(*a):
 
 
 # ------------------------------------------------------------------ synthetic inputs
-def sample_batch(sp, n_robots, device, min_ratio=0.1):
+def sample_batch(sp, n_robots, device, min_ratio=0.1, shard=0):
     """q ~ U(lo+0.1 range, hi-0.1 range), dq ~ U(-1,1); states whose task Jacobian has
     s_min/s_max < min_ratio are rejected before timing so the timed path is the non-singular one.
     The Jacobians of the candidates come from the library's own kinematics stage (input generation only)."""
@@ -54,7 +54,7 @@ def sample_batch(sp, n_robots, device, min_ratio=0.1):
     sp.capi.load_library().osc_builtin_model(ROBOT.encode(), C.byref(desc))
     n = desc.n
     lo = np.array(desc.q_lower[:n]); hi = np.array(desc.q_upper[:n])
-    rng = np.random.Generator(np.random.Philox(key=SEED))
+    rng = np.random.Generator(np.random.Philox(key=SEED + shard))   # counter-based: every shard regenerates its own slice
     q_ok = np.zeros((0, n)); dq_ok = np.zeros((0, n))
     tried = 0
     accepted = 0
@@ -252,7 +252,7 @@ def gpu_arm(args):
     global SEED
     SEED = 1234 + rank
     t_gen = time.time()
-    q, dq, rejected, rng = sample_batch(sp, R, local_rank, min_ratio=args.min_ratio)
+    q, dq, rejected, rng = sample_batch(sp, R, local_rank, min_ratio=args.min_ratio, shard=rank)
     log("[rank %d] sampled %d non-singular states (rejected fraction %.3f) in %.1fs" % (rank, R, rejected, time.time() - t_gen))
 
     # a dedicated (non-default) stream shared by torch and the library, so that torch.cuda.Event timing sees the kernels
