@@ -21,29 +21,67 @@ namespace sg {
 constexpr int MAXD = OSC_MAX_DOF;  // 8
 
 // ---- tiny dense helpers on row-major buffers with runtime sizes (rolled loops on purpose)
+// (two output columns per pass: two independent accumulation chains, half the loop overhead -- the general path runs with
+// one or two warps per scheduler and is bound by the latency of exactly these chains)
 static __device__ __noinline__ void mm(const double* A, int ar, int ac, const double* B, int bc, double* C) {	// C = A B
-	for (int i = 0; i < ar; i++)
-		for (int j = 0; j < bc; j++) {
+	for (int i = 0; i < ar; i++) {
+		int j = 0;
+		for (; j + 1 < bc; j += 2) {
+			double s0 = 0.0, s1 = 0.0;
+			for (int k = 0; k < ac; k++) {
+				const double a = A[i * ac + k];
+				s0 += a * B[k * bc + j];
+				s1 += a * B[k * bc + j + 1];
+			}
+			C[i * bc + j] = s0;
+			C[i * bc + j + 1] = s1;
+		}
+		if (j < bc) {
 			double s = 0.0;
 			for (int k = 0; k < ac; k++) s += A[i * ac + k] * B[k * bc + j];
 			C[i * bc + j] = s;
 		}
+	}
 }
 static __device__ __noinline__ void mm_at(const double* A, int ar, int ac, const double* B, int bc, double* C) {  // C = A^T B  (A: ar x ac, B: ar x bc)
-	for (int i = 0; i < ac; i++)
-		for (int j = 0; j < bc; j++) {
+	for (int i = 0; i < ac; i++) {
+		int j = 0;
+		for (; j + 1 < bc; j += 2) {
+			double s0 = 0.0, s1 = 0.0;
+			for (int k = 0; k < ar; k++) {
+				const double a = A[k * ac + i];
+				s0 += a * B[k * bc + j];
+				s1 += a * B[k * bc + j + 1];
+			}
+			C[i * bc + j] = s0;
+			C[i * bc + j + 1] = s1;
+		}
+		if (j < bc) {
 			double s = 0.0;
 			for (int k = 0; k < ar; k++) s += A[k * ac + i] * B[k * bc + j];
 			C[i * bc + j] = s;
 		}
+	}
 }
 static __device__ __noinline__ void mm_bt(const double* A, int ar, int ac, const double* B, int br, double* C) {  // C = A B^T  (B: br x ac)
-	for (int i = 0; i < ar; i++)
-		for (int j = 0; j < br; j++) {
+	for (int i = 0; i < ar; i++) {
+		int j = 0;
+		for (; j + 1 < br; j += 2) {
+			double s0 = 0.0, s1 = 0.0;
+			for (int k = 0; k < ac; k++) {
+				const double a = A[i * ac + k];
+				s0 += a * B[j * ac + k];
+				s1 += a * B[(j + 1) * ac + k];
+			}
+			C[i * br + j] = s0;
+			C[i * br + j + 1] = s1;
+		}
+		if (j < br) {
 			double s = 0.0;
 			for (int k = 0; k < ac; k++) s += A[i * ac + k] * B[j * ac + k];
 			C[i * br + j] = s;
 		}
+	}
 }
 static __device__ __noinline__ void mv(const double* A, int ar, int ac, const double* x, double* y) {
 	for (int i = 0; i < ar; i++) {
@@ -67,31 +105,34 @@ static __device__ __noinline__ double fro2(const double* A, int n) {
 // inverse of a symmetric positive definite matrix through its Cholesky factor (the reference uses
 // .inverse() / .llt().solve(I) on such matrices); returns false when not positive definite
 static __device__ __noinline__ bool spd_inverse(const double* A, int n, double* Ainv) {
-	double L[MAXD * MAXD];
+	double L[MAXD * MAXD], invl[MAXD];	// one division per pivot; the substitutions multiply by the reciprocal
 	bool ok = true;
 	for (int j = 0; j < n; j++) {
 		double d = A[j * n + j];
 		for (int k = 0; k < j; k++) d -= L[j * n + k] * L[j * n + k];
 		ok = ok && (d > 0.0);
 		const double l = sqrt(d);
+		const double il = 1.0 / l;
 		L[j * n + j] = l;
+		invl[j] = il;
 		for (int i = j + 1; i < n; i++) {
 			double s = A[i * n + j];
 			for (int k = 0; k < j; k++) s -= L[i * n + k] * L[j * n + k];
-			L[i * n + j] = s / l;
+			L[i * n + j] = s * il;
 		}
 	}
 	for (int c = 0; c < n; c++) {
 		double x[MAXD];
-		for (int i = 0; i < n; i++) {
+		for (int i = 0; i < c; i++) x[i] = 0.0;	 // column c of L^-1 starts at row c
+		for (int i = c; i < n; i++) {
 			double s = (i == c) ? 1.0 : 0.0;
-			for (int k = 0; k < i; k++) s -= L[i * n + k] * x[k];
-			x[i] = s / L[i * n + i];
+			for (int k = c; k < i; k++) s -= L[i * n + k] * x[k];
+			x[i] = s * invl[i];
 		}
 		for (int i = n - 1; i >= 0; i--) {
 			double s = x[i];
 			for (int k = i + 1; k < n; k++) s -= L[k * n + i] * x[k];
-			x[i] = s / L[i * n + i];
+			x[i] = s * invl[i];
 		}
 		for (int i = 0; i < n; i++) Ainv[i * n + c] = x[i];
 	}
