@@ -133,6 +133,42 @@ def test_config2_ragged_batch_sizes_multi_cycle(N):
         robot.setQ(q); robot.updateModel(); ob.set_state(q, dq)
 
 
+def test_config2_task_on_an_inner_link():
+    """the motion-force task on link6 of the Panda: joint 7 does not move the task frame, its Jacobian column is zero
+    (the masked iteration of the rolled Jacobian pass in the specialised kernel)"""
+    import sai_primitives_b200 as sp
+    from oracle.robots import make_chain
+    from oracle.sai_model import SaiModel
+    N = 160
+    link, pt = "link6", (0.05, 0.0, 0.02)
+    ch = make_chain("panda"); model = SaiModel(ch)
+    q = np.zeros((N, 7)); dq = np.zeros((N, 7))
+    for i in range(N):                                   # rejection sampling on this task's own Jacobian
+        g = rng_for(i, stream=31)
+        for _ in range(2000):
+            qi = ch.q_lower + (0.1 + 0.8 * g.random(7)) * (ch.q_upper - ch.q_lower)
+            model.setQ(qi); model.updateKinematics()
+            sv = np.linalg.svd(model.J(link, pt), compute_uv=False)
+            if sv[5] / sv[0] >= 0.09:
+                break
+        q[i] = qi; dq[i] = g.uniform(-1, 1, 7)
+    robot = sp.BatchedRobot("panda", N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    mft = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt)))
+    jt = sp.JointTask(robot)
+    ctrl = sp.RobotController(robot, [mft, jt])
+    ob = OracleBatch("panda", N); ob.set_state(q, dq)
+    omft = ob.add_mft(link, (np.eye(3), np.array(pt))); ojt = ob.add_jt(); ob.finalize()
+    _set_mft_goals(mft, omft, N); _set_joint_goals(jt, ojt, q, 7)
+    ctrl.updateControllerTaskModels()
+    tau = ctrl.computeControlTorques()
+    ref = ob.cycle()
+    st = robot.status()
+    assert (st & sp.capi.STATUS_UNHANDLED).sum() == 0
+    assert ((st & sp.capi.STATUS_SINGULAR_PATH) == 0).mean() > 0.9
+    assert rel_err(tau, ref).max() < REL_TOL
+
+
 def test_config2_gravity_and_saturation():
     import sai_primitives_b200 as sp
     N = 64
