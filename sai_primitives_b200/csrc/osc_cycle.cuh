@@ -74,11 +74,16 @@ DEVI void bie_cholesky_from_factor(const double (&L)[N][N], const double (&d)[N]
 // reduced Jacobian columns and the gravity vector.
 template <int N>
 constexpr int kSmFactor = N * (N + 1) / 2 + N;
-template <int N, int R, bool SPEC = false>
+template <int N, int R, bool SPEC = false, bool MOTION = SPEC>
 constexpr int cycle_smem_doubles() {
 	// rolled kinematics layout (osc_kindyn.cuh); factor and Jacobian columns fit underneath, the staged goals of the
 	// motion-force task (30) go behind the Jacobian columns, those of the joint task (6 N) later take their place
-	if (SPEC) return (15 * N > kSmFactor<N> + N * R + 30) ? 15 * N : kSmFactor<N> + N * R + 30;
+	if (SPEC) {
+		int d = 15 * N;
+		if (MOTION && kSmFactor<N> + N * R + 30 > d) d = kSmFactor<N> + N * R + 30;
+		if (kSmFactor<N> + 6 * N > d) d = kSmFactor<N> + 6 * N;
+		return d;
+	}
 	return (9 * N > kSmFactor<N> + N * R + N) ? 9 * N : kSmFactor<N> + N * R + N;
 }
 static_assert(kSmFactor<8> + 8 * 6 <= 15 * 8 && kSmFactor<8> <= 9 * 8, "rolled layout: the Jacobian columns must not run into live joint data");
@@ -176,7 +181,10 @@ DEVI void prefetch_block_rows(const OscProgram& P, uint64_t blk) {
 // no longer stays in the SM's instruction cache between blocks and every 256-byte line costs a round trip to L2
 // (profiles/r01_ifetch.md).  Robots whose bounded-inertia update has rank two or more leave through the general path.
 // GRAV (with SPEC only): gravity compensation compiled in; the non-specialised instantiations test the run-time flag.
-template <int N, int R, bool HAS_JT, bool FULL, bool SPEC = false, bool GRAV = false>
+// MOTION (with SPEC only; default): the motion-force task is a full task under pure motion control, so only the two PID
+// laws are compiled in and its goals are staged through shared memory.  SPEC without MOTION keeps the general control
+// law (partial tasks, force / moment spaces, closed loops, POPC) on top of the same rolled kinematics.
+template <int N, int R, bool HAS_JT, bool FULL, bool SPEC = false, bool GRAV = false, bool MOTION = SPEC>
 __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(const __grid_constant__ OscProgram P) {
 	extern __shared__ double sm[];
 	// Programmatic dependent launch on both sides: the general-path kernel of this cycle may be scheduled into whatever
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				for (int b = 0; b < R; b++) G[a][b] = 0.0;
 			if constexpr (SPEC) {
 				// rolled: axis, origin and velocity of joint j from shared memory
-				static_assert(!SPEC || (R == 6 && FULL), "the specialisation is the full six-dof task");
+				static_assert(!MOTION || (R == 6 && FULL), "pure motion control is specialised for the full six-dof task");
 				const int nb = t.body + 1;	// joints beyond the task body do not move it
 #pragma unroll 1
 				for (int j = 0; j < N; j++) {
@@ -333,19 +341,20 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 					const double dqj = dqr[0];	// rotate the register file: no run-time register index
 #pragma unroll
 					for (int k = 0; k + 1 < N; k++) dqr[k] = dqr[k + 1];
-					double cr[6];
-					cross3(a3, d, cr);
-					cr[0] *= mk;
-					cr[1] *= mk;
-					cr[2] *= mk;
-					cr[3] = a3[0] * mk;
-					cr[4] = a3[1] * mk;
-					cr[5] = a3[2] * mk;
+					double c6[6], cr[R];
+					cross3(a3, d, c6);
+					c6[0] *= mk;
+					c6[1] *= mk;
+					c6[2] *= mk;
+					c6[3] = a3[0] * mk;
+					c6[4] = a3[1] * mk;
+					c6[5] = a3[2] * mk;
 #pragma unroll
 					for (int k = 0; k < 3; k++) {
-						v[k] += cr[k] * dqj;
-						w[k] += cr[3 + k] * dqj;
+						v[k] += c6[k] * dqj;
+						w[k] += c6[3 + k] * dqj;
 					}
+					reduce_task_vector<R, FULL>(t, c6, cr);
 					double* Jj = Js + (size_t)(j * R) * sms;
 #pragma unroll
 					for (int a = 0; a < R; a++) Jj[a * sms] = cr[a];
@@ -355,7 +364,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 						for (int b = 0; b <= a; b++) G[a][b] += cr[a] * cr[b];
 				}
 			}
-			if constexpr (SPEC) mft_stage_goals(t, NR, i, smt + (size_t)(kSmFactor<N> + N * R) * sms, sms);
+			if constexpr (MOTION) mft_stage_goals(t, NR, i, smt + (size_t)(kSmFactor<N> + N * R) * sms, sms);
 #pragma unroll
 			for (int j = 0; j < (SPEC ? 0 : N); j++) {
 				double c6[6], cr[R];
@@ -422,8 +431,8 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 			double fstar[6] = {0, 0, 0, 0, 0, 0}, F[6] = {0, 0, 0, 0, 0, 0};
 			has_F = true;
 			if (alive)
-				has_F = mft_control_law<SPEC>(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status,
-											  SPEC ? smt + (size_t)(kSmFactor<N> + N * R) * sms : nullptr, sms);
+				has_F = mft_control_law<MOTION>(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status,
+												MOTION ? smt + (size_t)(kSmFactor<N> + N * R) * sms : nullptr, sms);
 			reduce_task_vector<R, FULL>(t, fstar, yf);
 			reduce_task_vector<R, FULL>(t, F, yF);
 		}

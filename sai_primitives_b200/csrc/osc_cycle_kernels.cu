@@ -39,7 +39,8 @@ static double min_eig_sym3(const double* I) {
 }
 
 // Conditions under which the specialised instantiation (SPEC, osc_cycle.cuh) computes the same thing as the general one.
-static bool cycle_spec_eligible(const OscProgram& P, bool has_jt) {
+// *motion: the motion-force task additionally is a full task under pure motion control (the MOTION flag of the kernel)
+static bool cycle_spec_eligible(const OscProgram& P, bool has_jt, bool* motion) {
 	const DevModel& m = P.model;
 	for (int j = 0; j < m.n; j++)
 		if (m.jtype[j] != 0 || m.axis[j][0] != 0.0 || m.axis[j][1] != 0.0 || m.axis[j][2] != 1.0) return false;
@@ -62,9 +63,9 @@ static bool cycle_spec_eligible(const OscProgram& P, bool has_jt) {
 	}
 	const DevMft& t = P.mft[0];
 	const osc_mft_params& p = t.p;
-	if (!t.full || p.force_space_dimension != 0 || p.moment_space_dimension != 0 || p.closed_loop_force_control ||
-		p.closed_loop_moment_control || p.use_velocity_saturation || p.dynamic_decoupling_type == OSC_IMPEDANCE)
-		return false;
+	if (p.use_velocity_saturation || p.dynamic_decoupling_type == OSC_IMPEDANCE) return false;
+	*motion = t.full && p.force_space_dimension == 0 && p.moment_space_dimension == 0 && !p.closed_loop_force_control &&
+			  !p.closed_loop_moment_control;
 	if (has_jt) {
 		const DevJt& j = P.jt[0];
 		if (!j.full || j.p.use_velocity_saturation || j.p.dynamic_decoupling_type == OSC_IMPEDANCE) return false;
@@ -72,15 +73,15 @@ static bool cycle_spec_eligible(const OscProgram& P, bool has_jt) {
 	return true;
 }
 
-template <int N, int R, bool JT, bool FULL, bool SPEC = false, bool GRAV = false>
+template <int N, int R, bool JT, bool FULL, bool SPEC = false, bool GRAV = false, bool MOTION = SPEC>
 static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 	const unsigned grid = (unsigned)((P.n_robots + kCycleBlock - 1) / kCycleBlock);
-	constexpr int smem = cycle_smem_doubles<N, R, SPEC>() * kCycleBlock * (int)sizeof(double);
+	constexpr int smem = cycle_smem_doubles<N, R, SPEC, MOTION>() * kCycleBlock * (int)sizeof(double);
 	static bool configured[64] = {false};  // per device: function attributes belong to the device's context
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev < 0 || dev >= 64 || !configured[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(osc_cycle_kernel<N, R, JT, FULL, SPEC, GRAV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaError_t e = cudaFuncSetAttribute(osc_cycle_kernel<N, R, JT, FULL, SPEC, GRAV, MOTION>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e != cudaSuccess) return e;
 		if (dev >= 0 && dev < 64) configured[dev] = true;
 	}
@@ -104,7 +105,7 @@ static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 		attr[0].val.programmaticStreamSerializationAllowed = 1;
 		cfg.attrs = attr;
 		cfg.numAttrs = 1;
-		cudaError_t e = cudaLaunchKernelEx(&cfg, osc_cycle_kernel<N, R, JT, FULL, SPEC, GRAV>, P);
+		cudaError_t e = cudaLaunchKernelEx(&cfg, osc_cycle_kernel<N, R, JT, FULL, SPEC, GRAV, MOTION>, P);
 		if (e != cudaSuccess) return e;
 	}
 #if defined(OSC_TRACE)
@@ -127,10 +128,21 @@ template <int N, int R, bool JT>
 static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 	cudaError_t e0;
 	if constexpr (R == 6) {
-		if (P.mft[0].full)
-			e0 = !cycle_spec_eligible(P, JT) ? launch_variant<N, R, JT, true>(P, stream)
-				 : P.gravity_comp		   ? launch_variant<N, R, JT, true, true, true>(P, stream)
-										   : launch_variant<N, R, JT, true, true, false>(P, stream);
+		bool motion = false;
+		const bool spec = cycle_spec_eligible(P, JT, &motion);
+		if (!P.mft[0].full)
+			e0 = launch_variant<N, R, JT, false>(P, stream);
+		else if (spec && motion)
+			e0 = P.gravity_comp ? launch_variant<N, R, JT, true, true, true>(P, stream) : launch_variant<N, R, JT, true, true, false>(P, stream);
+		else if (spec && !P.gravity_comp)
+			e0 = launch_variant<N, R, JT, true, true, false, false>(P, stream);  // full task with force / moment control
+		else
+			e0 = launch_variant<N, R, JT, true>(P, stream);
+	} else if constexpr (R == 3) {
+		// the other common shape: three controlled directions (position only, or a planar task), any control law
+		bool motion = false;
+		if (cycle_spec_eligible(P, JT, &motion) && !P.gravity_comp)
+			e0 = launch_variant<N, R, JT, false, true, false, false>(P, stream);
 		else
 			e0 = launch_variant<N, R, JT, false>(P, stream);
 	} else {
