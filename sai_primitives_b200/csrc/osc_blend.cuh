@@ -21,8 +21,58 @@
 
 namespace osc {
 
-// Cyclic Jacobi eigen-decomposition of a symmetric 6 x 6 matrix held in registers: G -> diag(lambda), U <- eigenvectors
-// (columns).  Converges quadratically; the sweep loop is per thread (warp divergence = the slowest lane).
+// Jacobi eigen-decomposition of a symmetric 6 x 6 matrix held in registers: G -> diag(lambda), U <- eigenvectors (columns).
+// Parallel (round-robin) ordering: a sweep is five rounds of three rotations on disjoint index pairs.  The three rotation
+// angles of a round come from the same matrix, so their scalar chains (reciprocal, two square roots: ~30 dependent FP64
+// operations each) overlap instead of following one another, and the rotations are branch-free (c = 1, s = 0 where the
+// off-diagonal entry is already negligible): no divergence inside a sweep.  The sweep loop is per thread (warp
+// divergence = the slowest lane).
+template <int P, int Q>
+DEVI void jacobi_angle(const double (&G)[6][6], double& c, double& s) {
+	const double gpq = G[P][Q];
+	const bool rot = fabs(gpq) > 1e-18 * (fabs(G[P][P]) + fabs(G[Q][Q]));
+	const double g = rot ? gpq : 1.0;
+	// lean reciprocal / square roots (osc_math.cuh): g is non-zero and both radicands are >= 1
+	const double theta = (G[Q][Q] - G[P][P]) * (0.5 * rcp_nz(g));
+	const double t = (theta >= 0.0 ? 1.0 : -1.0) * rcp_nz(fabs(theta) + sqrt_pos(theta * theta + 1.0));
+	const double cc = rsqrt_pos(t * t + 1.0);
+	c = rot ? cc : 1.0;
+	s = rot ? t * cc : 0.0;
+}
+template <int P, int Q>
+DEVI void jacobi_cols(double (&A)[6][6], double c, double s) {	// A <- A J(P, Q)
+#pragma unroll
+	for (int k = 0; k < 6; k++) {
+		const double akp = A[k][P], akq = A[k][Q];
+		A[k][P] = c * akp - s * akq;
+		A[k][Q] = s * akp + c * akq;
+	}
+}
+template <int P, int Q>
+DEVI void jacobi_rows(double (&A)[6][6], double c, double s) {	// A <- J(P, Q)^T A
+#pragma unroll
+	for (int k = 0; k < 6; k++) {
+		const double apk = A[P][k], aqk = A[Q][k];
+		A[P][k] = c * apk - s * aqk;
+		A[Q][k] = s * apk + c * aqk;
+	}
+}
+template <int P0, int Q0, int P1, int Q1, int P2, int Q2>
+DEVI void jacobi_round(double (&G)[6][6], double (&U)[6][6]) {
+	double c0, s0, c1, s1, c2, s2;
+	jacobi_angle<P0, Q0>(G, c0, s0);
+	jacobi_angle<P1, Q1>(G, c1, s1);
+	jacobi_angle<P2, Q2>(G, c2, s2);
+	jacobi_cols<P0, Q0>(G, c0, s0);
+	jacobi_cols<P1, Q1>(G, c1, s1);
+	jacobi_cols<P2, Q2>(G, c2, s2);
+	jacobi_rows<P0, Q0>(G, c0, s0);
+	jacobi_rows<P1, Q1>(G, c1, s1);
+	jacobi_rows<P2, Q2>(G, c2, s2);
+	jacobi_cols<P0, Q0>(U, c0, s0);
+	jacobi_cols<P1, Q1>(U, c1, s1);
+	jacobi_cols<P2, Q2>(U, c2, s2);
+}
 DEVI void jacobi_eig6(double (&G)[6][6], double (&U)[6][6]) {
 #pragma unroll
 	for (int a = 0; a < 6; a++)
@@ -38,37 +88,11 @@ DEVI void jacobi_eig6(double (&G)[6][6], double (&U)[6][6]) {
 		}
 		// off-diagonal entries at 1e-15 of the diagonal scale: the rounding floor of the rotations is ~1e-16
 		if (off <= 1e-30 * dia) break;
-#pragma unroll
-		for (int p = 0; p < 5; p++)
-#pragma unroll
-			for (int q = p + 1; q < 6; q++) {
-				const double gpq = G[p][q];
-				if (fabs(gpq) > 1e-18 * (fabs(G[p][p]) + fabs(G[q][q]))) {
-					// lean reciprocal / square roots (osc_math.cuh): gpq is non-zero here and both radicands are >= 1; the
-					// library versions cost about a hundred instructions per rotation with their special-case branches
-					const double theta = (G[q][q] - G[p][p]) * (0.5 * rcp_nz(gpq));
-					const double t = (theta >= 0.0 ? 1.0 : -1.0) * rcp_nz(fabs(theta) + sqrt_pos(theta * theta + 1.0));
-					const double c = rsqrt_pos(t * t + 1.0), s = t * c;
-#pragma unroll
-					for (int k = 0; k < 6; k++) {  // G <- G J
-						const double gkp = G[k][p], gkq = G[k][q];
-						G[k][p] = c * gkp - s * gkq;
-						G[k][q] = s * gkp + c * gkq;
-					}
-#pragma unroll
-					for (int k = 0; k < 6; k++) {  // G <- J^T G
-						const double gpk = G[p][k], gqk = G[q][k];
-						G[p][k] = c * gpk - s * gqk;
-						G[q][k] = s * gpk + c * gqk;
-					}
-#pragma unroll
-					for (int k = 0; k < 6; k++) {
-						const double ukp = U[k][p], ukq = U[k][q];
-						U[k][p] = c * ukp - s * ukq;
-						U[k][q] = s * ukp + c * ukq;
-					}
-				}
-			}
+		jacobi_round<0, 5, 1, 4, 2, 3>(G, U);
+		jacobi_round<0, 4, 3, 5, 1, 2>(G, U);
+		jacobi_round<0, 3, 2, 4, 1, 5>(G, U);
+		jacobi_round<0, 2, 1, 3, 4, 5>(G, U);
+		jacobi_round<0, 1, 2, 5, 3, 4>(G, U);
 	}
 }
 
