@@ -150,6 +150,9 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 	}
 	if (e0 != cudaSuccess) return e0;
 	if constexpr (R > 0) {
+#ifdef OSC_TUNE_SKIP_GENERAL
+		return e0;	// tuning builds only: measure what the second launch costs when the hand-over list is empty
+#endif
 		// The general path for the robots the fast kernel handed over (usually none or few).  One block per SM,
 		// grid-stride over the compacted list; launched with programmatic stream serialization so that its launch
 		// latency overlaps the tail of the fast kernel (it waits on griddepcontrol.wait before reading the list).
