@@ -162,9 +162,11 @@ DEVI void prefetch_block_rows(const OscProgram& P, uint64_t blk) {
 		}
 	}
 	if (row) {
+		// 16-byte granules strictly inside [first robot, last robot] of the row: nothing outside the caller's buffer is named
 		const uint64_t a0 = (uint64_t)(row + b0 * esz);
-		const uint64_t a = a0 & ~(uint64_t)15;
-		const uint32_t bytes = (uint32_t)((a0 - a) + (uint64_t)cnt * esz) & ~15u;  // stays inside the row's allocation
+		const uint64_t a = (a0 + 15) & ~(uint64_t)15;
+		const uint64_t end = a0 + (uint64_t)cnt * esz;
+		const uint32_t bytes = (end > a) ? (uint32_t)((end - a) & ~(uint64_t)15) : 0u;
 		if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
 	}
 }
