@@ -285,6 +285,14 @@ int64_t osc_launch_count(const osc_handle* h);
  * For the link frame + point of motion-force task `task_id` (or, when task_id < 0, of `frame` and `point`):
  *   M (n*n, row-major), J (6*n row-major, linear rows first: SaiModel::JWorldFrame), x (3), R (9), g (n).
  * Any output pointer may be NULL. */
+/* ---- test probe: n_steps consecutive POPCExplicitForceControl::computePassivitySaturatedForce calls
+ * (POPCExplicitForceControl.cpp:30-96, kv_force = kv * I as MotionForceTask.h:308 builds it) on the POPC state of every
+ * robot of the task, host inputs n_steps x 3 row major shared by all robots, out = the results of robot 0.  Passivity
+ * must be enabled on the task.  Lets the device code be checked against vectors produced by the reference's own source
+ * (tests/golden/popc_reference.npz). ---- */
+int osc_debug_popc_sequence(osc_handle* h, int task_id, int n_steps, const double* fd, const double* fs, const double* vcl,
+							const double* vr, double kv_force, double kff_force, double* out);
+
 /* ---- measurement aid (no reference counterpart): sustained FP64 FMA rate of the device in TFLOP/s, from a DFMA-only
  * kernel run for about `seconds` (bench.py reports the roofline against it next to the datasheet figure) ---- */
 int osc_measure_fp64_peak(osc_handle* h, double seconds, double* tflops_out);

@@ -178,6 +178,7 @@ SYMBOLS = {
     "osc_urdf_register": (C.c_int, [C.c_char_p, C.c_char_p]),
     "osc_urdf_register_file": (C.c_int, [C.c_char_p, C.c_char_p]),
     "osc_urdf_last_error": (C.c_char_p, []),
+    "osc_debug_popc_sequence": (C.c_int, [_H, C.c_int, C.c_int, _PD, _PD, _PD, _PD, C.c_double, C.c_double, _PD]),
     "osc_measure_fp64_peak": (C.c_int, [_H, C.c_double, _PD]),
     "osc_sim_integrate": (C.c_int, [_H, _PD, _PD, _PD, C.c_double, C.c_int, C.c_int]),
     "osc_eval_model": (C.c_int, [_H, C.c_int, C.POINTER(LinkFrame), C.POINTER(D), _PD, _PD, _PD, _PD, _PD, C.c_int]),

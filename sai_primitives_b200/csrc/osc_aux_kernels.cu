@@ -22,6 +22,11 @@ cudaError_t launch_reinit_mft(const OscProgram& P, int mft_index, int full_init,
 	DISPATCH_N(P.model.n, (reinit_mft_kernel<N_><<<grid_for(P.n_robots, 128), 128, 0, stream>>>(P, mft_index, full_init)));
 	return cudaGetLastError();
 }
+cudaError_t launch_popc_probe(const OscProgram& P, int mft_index, int K, const double* fd, const double* fs, const double* vcl, const double* vr,
+							  double kv, double kff, double* out, cudaStream_t stream) {
+	popc_probe_kernel<<<grid_for(P.n_robots, 128), 128, 0, stream>>>(P, mft_index, K, fd, fs, vcl, vr, kv, kff, out);
+	return cudaGetLastError();
+}
 cudaError_t measure_fp64_peak(double seconds, double* tflops, cudaStream_t stream) {
 	int dev = 0, sms = 0;
 	cudaGetDevice(&dev);

@@ -388,6 +388,32 @@ __global__ void __launch_bounds__(128) sim_integrate_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// Test probe for SURVEY.md row a12: K consecutive popc_step calls (the device code the fused kernels inline) on the
+// POPC state of every robot of a motion-force task, with caller-supplied inputs (K x 3 each, row major, the same for
+// all robots).  tests/test_popc_reference.py feeds it the sequence of tests/golden/popc_reference.npz, whose expected
+// outputs were produced by the reference's own POPCExplicitForceControl.cpp.
+__global__ void popc_probe_kernel(const __grid_constant__ OscProgram P, int mft_index, int K, const double* fd, const double* fs, const double* vcl,
+								   const double* vr, double kv, double kff, double* out) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t NR = P.n_robots;
+	if (i >= NR) return;
+	const DevMft& t = P.mft[mft_index];
+	uint32_t status = 0;
+	for (int k = 0; k < K; k++) {
+		const double a[3] = {fd[3 * k], fd[3 * k + 1], fd[3 * k + 2]}, b[3] = {fs[3 * k], fs[3 * k + 1], fs[3 * k + 2]};
+		const double c[3] = {vcl[3 * k], vcl[3 * k + 1], vcl[3 * k + 2]}, d[3] = {vr[3 * k], vr[3 * k + 1], vr[3 * k + 2]};
+		double o[3];
+		popc_step(t, NR, i, a, b, c, d, kv, kff, o, status);
+		if (i == 0) {
+			out[3 * k] = o[0];
+			out[3 * k + 1] = o[1];
+			out[3 * k + 2] = o[2];
+		}
+	}
+	if (status) P.status[i] |= status;
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 FMA issue-rate probe for the roofline denominator (SURVEY.md 8d asks for a measured FP64 figure next to the
 // datasheet one): eight independent DFMA chains per thread in a rolled loop, every SM full.
 __global__ void __launch_bounds__(1024) fp64_peak_kernel(double* out, double a, double b, int iters) {

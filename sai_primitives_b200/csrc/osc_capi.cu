@@ -1047,6 +1047,31 @@ static int step_impl(osc_handle* h, const double* q, const double* dq, double* t
 	return run_cycle(h, tau_out, mem_kind, sync_host);
 }
 
+int osc_debug_popc_sequence(osc_handle* h, int task_id, int n_steps, const double* fd, const double* fs, const double* vcl, const double* vr,
+							double kv_force, double kff_force, double* out) {
+	ENTER(h);
+	int rc = check_task(h, task_id, OSC_TASK_MOTION_FORCE);
+	if (rc != OSC_OK) return rc;
+	if (n_steps < 1 || !fd || !fs || !vcl || !vr || !out) return fail(h, OSC_ERR_INVALID_ARGUMENT, "bad argument");
+	const int idx = h->tasks[task_id].index;
+	if (!h->prog.mft[idx].p.passivity_enabled || !h->prog.mft[idx].ring) return fail(h, OSC_ERR_STATE, "passivity is not enabled on this task");
+	const size_t bytes = (size_t)3 * n_steps * sizeof(double);
+	double* d = nullptr;
+	CUDA_TRY(h, cudaMalloc(&d, 5 * bytes));
+	const double* src[4] = {fd, fs, vcl, vr};
+	cudaError_t e = cudaSuccess;
+	for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaMemcpyAsync(d + (size_t)k * 3 * n_steps, src[k], bytes, cudaMemcpyHostToDevice, h->stream);
+	if (e == cudaSuccess)
+		e = osc::launch_popc_probe(h->prog, idx, n_steps, d, d + (size_t)3 * n_steps, d + (size_t)6 * n_steps, d + (size_t)9 * n_steps, kv_force, kff_force,
+								   d + (size_t)12 * n_steps, h->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + (size_t)12 * n_steps, bytes, cudaMemcpyDeviceToHost, h->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+	cudaFree(d);
+	CUDA_TRY(h, e);
+	h->launches += 1;
+	return OSC_OK;
+}
+
 int osc_measure_fp64_peak(osc_handle* h, double seconds, double* tflops_out) {
 	ENTER(h);
 	if (!tflops_out || !(seconds > 0.0)) return fail(h, OSC_ERR_INVALID_ARGUMENT, "bad argument");

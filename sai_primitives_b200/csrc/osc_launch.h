@@ -24,6 +24,8 @@ constexpr int kCycleBlock = OSC_CYCLE_BLOCK;
 cudaError_t launch_cycle(int n, int R, bool has_jt, const OscProgram& P, cudaStream_t stream);
 bool cycle_signature_available(int n, int R, bool has_jt);
 
+cudaError_t launch_popc_probe(const OscProgram& P, int mft_index, int K, const double* fd, const double* fs, const double* vcl, const double* vr,
+							  double kv, double kff, double* out, cudaStream_t stream);
 cudaError_t measure_fp64_peak(double seconds, double* tflops, cudaStream_t stream);
 cudaError_t launch_sim_integrate(const OscProgram& P, double* q, double* dq, const double* tau, double dt, int substeps, cudaStream_t stream);
 cudaError_t launch_jla(const OscProgram& P, cudaStream_t stream);
