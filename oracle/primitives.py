@@ -4,6 +4,10 @@ reference control law, statement by statement.
 PARITY UNPINNED: the reference has no tests / golden vectors for this path and
 cannot be built here (needs Eigen + sai-model); this file follows the reference
 SOURCE line by line instead, each function citing the file:line it follows.
+Exception: POPCExplicitForceControl below is pinned -- the reference's own
+POPCExplicitForceControl.cpp compiles against a small stand-in for the Eigen types
+it uses (oracle/Makefile, oracle/_ref) and tests/test_popc_reference.py holds this
+class to its outputs (tests/golden/popc_reference.npz) to 1e-12.
 Internal OTG (Ruckig) is excluded (BASELINE.json north_star) and defaults OFF.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import
