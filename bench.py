@@ -473,7 +473,7 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--robots", type=int, default=65536, help="robots per GPU (BASELINE config 2: 65,536)")
     ap.add_argument("--sets", type=int, default=8, help="controller instances used round-robin (working set > L2)")
