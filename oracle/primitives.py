@@ -484,8 +484,16 @@ class JointTask:
     def getTaskNullspace(self):
         return self._N
 
+    def getPreviousTasksNullspace(self):                          # JointTask.h:223
+        return self._N_prec
+
     def getTaskAndPreviousNullspace(self):                        # JointTask.h:224-226
         return self._N @ self._N_prec
+
+    # JointTask.h:108-190
+    def getCurrentPosition(self): return self._current_position
+    def getCurrentVelocity(self): return self._current_velocity
+    def getGoalPosition(self): return self._goal_position
 
     def updateTaskModel(self, N_prec):                            # :218-283
         robot = self._robot
@@ -838,8 +846,16 @@ class MotionForceTask:
         return P @ (np.eye(3) - self.sigmaMoment()) @ P.T
 
     def getTaskNullspace(self): return self._N
+    def getPreviousTasksNullspace(self): return self._N_prec                  # MotionForceTask.h:206
     def getTaskAndPreviousNullspace(self): return self._N @ self._N_prec      # MotionForceTask.h:207-209
     def getUnitMassForce(self): return self._unit_mass_force
+    # MotionForceTask.h:116-140, :540-546
+    def getCurrentPosition(self): return self._current_position
+    def getCurrentOrientation(self): return self._current_orientation
+    def getCurrentLinearVelocity(self): return self._current_linear_velocity
+    def getCurrentAngularVelocity(self): return self._current_angular_velocity
+    def getPositionError(self): return self.sigmaPosition() @ (self._goal_position - self._current_position)
+    def getOrientationError(self): return self.sigmaOrientation() @ self._orientation_error
 
     def updateTaskModel(self, N_prec):                            # :247-268
         robot = self._robot

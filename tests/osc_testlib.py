@@ -1,5 +1,14 @@
 """Shared helpers of the parity tests: seeded synthetic inputs and
-oracle-vs-CUDA comparison.  The oracle (oracle/) is used here ONLY as the checker."""
+oracle-vs-CUDA comparison.  The oracle (oracle/) is used here ONLY as the checker.
+
+Two checkers exist:
+  "reference"  oracle/_ref/libsai_ref_orient.so -- the reference's OWN JointTask / MotionForceTask / SingularityHandler /
+               JointLimitAvoidanceTask / RobotController / POPC sources compiled where they lie (oracle/sai_ref.py);
+  "numpy"      oracle/primitives.py -- the statement-by-statement restatement.
+`OracleBatch(...)` hands out the reference whenever the library is present (it is built in this container and travels to the
+GPU box) and the numpy restatement otherwise; OSC_ORACLE=numpy|reference forces one."""
+import os
+
 import numpy as np
 
 from oracle import primitives as OP
@@ -69,8 +78,25 @@ def rel_err(a, b):
     return np.abs(a - b).reshape(a.shape[0], -1).max(axis=1) / scale
 
 
-class OracleBatch:
-    """N independent oracle robots with the same hierarchy (the CPU reference looped over the batch)."""
+def oracle_kind():
+    forced = os.environ.get("OSC_ORACLE")
+    if forced:
+        return forced
+    from oracle import sai_ref
+    return "reference" if sai_ref.available(oriented=True) else "numpy"
+
+
+def OracleBatch(robot_name, n_robots, T_world_robot=None, kind=None):
+    """N independent CPU controllers with the same hierarchy: the reference's compiled control law when available"""
+    kind = kind or oracle_kind()
+    if kind == "reference":
+        from oracle.sai_ref import RefBatch
+        return RefBatch(robot_name, n_robots, T_world_robot=T_world_robot, oriented=True)
+    return NumpyOracleBatch(robot_name, n_robots, T_world_robot=T_world_robot)
+
+
+class NumpyOracleBatch:
+    """N independent oracle robots with the same hierarchy (the CPU restatement looped over the batch)."""
 
     def __init__(self, robot_name, n_robots, T_world_robot=None):
         self.chain = make_chain(robot_name)
@@ -82,7 +108,7 @@ class OracleBatch:
         for r, qi, dqi in zip(self.robots, q, dq):
             r.setQ(qi); r.setDq(dqi); r.updateModel()
 
-    def add_mft(self, link, compliant, dirs_t=None, dirs_r=None, in_compliant=False, dt=0.001, name="motion_force_task"):
+    def add_mft(self, link, compliant=None, dirs_t=None, dirs_r=None, in_compliant=False, dt=0.001, name="motion_force_task"):
         out = []
         for i, r in enumerate(self.robots):
             t = OP.MotionForceTask(r, link, compliant, dirs_t, dirs_r, task_name=name,
