@@ -1,9 +1,15 @@
-"""Generates tests/golden/*.npz from the numpy restatement (oracle/primitives.py).
+"""Generates tests/golden/config*.npz FROM THE REFERENCE'S OWN COMPILED CONTROL LAW.
 
-PARITY UNPINNED: the reference ships no golden vectors and cannot be run here, so
-these fixtures freeze the ORACLE's outputs (not the reference's) on seeded inputs.  They pin the
-oracle against accidental change and give the CUDA path a check that does not need the oracle at
-run time.  Regenerate with:  python tests/golden/generate.py
+Source: oracle/_ref/libsai_ref_orient.so = /root/reference/src/{RobotController,tasks/JointTask,tasks/MotionForceTask,
+tasks/SingularityHandler,tasks/JointLimitAvoidanceTask,helper_modules/POPCExplicitForceControl,...}.cpp compiled where they
+lie, unmodified (oracle/Makefile, oracle/sai_ref.py); the model arithmetic under it is the sai-model stand-in.  The reference
+ships no golden vectors of its own, so these are "outputs of the reference itself run here".  Each file records
+`source`.  Where the singular branch is exercised the file also holds `tau_eigen_signs`: the same run with the stand-in's
+JacobiSVD left at the signs Eigen's published algorithm produces (libsai_ref.so) instead of this repository's orientation
+convention, and `sign_sensitive`: the robots whose torques differ between the two (classifySingularity perturbs q along
++V_s, SingularityHandler.cpp:254, so type-1/type-2 depends on the sign of the singular vector).
+
+Regenerate with:  python tests/golden/generate.py      (needs /root/reference; `--source numpy` freezes the restatement instead)
 """
 import os
 import sys
@@ -13,9 +19,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from tests.osc_testlib import TASK_POINTS, OracleBatch, rng_for, rot_exp, sample_states  # noqa: E402
+from tests import osc_testlib  # noqa: E402
+from tests.osc_testlib import TASK_POINTS, rng_for, rot_exp, sample_states, sensed_ex09  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
+SOURCE = "reference"   # "reference": oracle/_ref/libsai_ref_orient.so; "numpy": oracle/primitives.py
+
+
+def OracleBatch(name, N, eigen_signs=False):
+    if SOURCE == "reference" and eigen_signs:
+        from oracle.sai_ref import RefBatch
+        return RefBatch(name, N, oriented=False)
+    return osc_testlib.OracleBatch(name, N, kind=SOURCE)
+
+
+def source_tag():
+    return np.array("reference: /root/reference/src compiled in place (oracle/_ref/libsai_ref_orient.so)" if SOURCE == "reference"
+                    else "numpy restatement (oracle/primitives.py)")
 
 
 def goals_for(N, n, x0, R0, q, stream):
@@ -49,23 +69,38 @@ def config1():
         qd[i] = q[i] + rng_for(i, stream=31).uniform(-0.2, 0.2, 7)
         t.setGoalPosition(qd[i])
     tau = np.array([ob.cycle() for _ in range(3)])
-    np.savez(os.path.join(OUT, "config1_joint_task.npz"), q=q, dq=dq, qd=qd, tau=tau)
+    np.savez(os.path.join(OUT, "config1_joint_task.npz"), q=q, dq=dq, qd=qd, tau=tau, source=source_tag())
+
+
+def _osc_run(name, N, q, dq, dt_, dr_, stream, eigen_signs=False):
+    link, pt = TASK_POINTS[name]
+    ob = OracleBatch(name, N, eigen_signs=eigen_signs); ob.set_state(q, dq)
+    omft = ob.add_mft(link, (np.eye(3), np.array(pt)), dt_, dr_); ojt = ob.add_jt(); ob.finalize()
+    x0 = np.array([t._current_position for t in omft]); R0 = np.array([t._current_orientation for t in omft])
+    G = goals_for(N, q.shape[1], x0, R0, q, stream)
+    apply_goals(omft, ojt, G)
+    tau = np.array([ob.cycle() for _ in range(3)])
+    singular = np.array([len(t._singularity_handler._singularity_types) != 0 for t in omft])
+    s = [np.asarray(t._singularity_handler._svd_s) for t in omft]
+    smin = np.array([x[-1] / x[0] for x in s])
+    return tau, singular, smin, x0, R0, G
+
+
+def _sign_sensitive(tau, tau_e):
+    return (np.abs(tau - tau_e).max(axis=(0, 2)) > 1e-9 * np.maximum(np.abs(tau).max(axis=(0, 2)), 1e-9))
 
 
 def config2():
     """Panda, MotionForceTask 6-DoF + JointTask null space via RobotController, defaults (BIE); includes singular states"""
     N = 32
     q, dq, _ = sample_states("panda", N)     # unfiltered: ~half of the robots take the blending branch
-    link, pt = TASK_POINTS["panda"]
-    ob = OracleBatch("panda", N); ob.set_state(q, dq)
-    omft = ob.add_mft(link, (np.eye(3), np.array(pt))); ojt = ob.add_jt(); ob.finalize()
-    x0 = np.array([t._current_position for t in omft]); R0 = np.array([t._current_orientation for t in omft])
-    G = goals_for(N, 7, x0, R0, q, 32)
-    apply_goals(omft, ojt, G)
-    tau = np.array([ob.cycle() for _ in range(3)])
-    singular = np.array([len(t._singularity_handler._singularity_types) != 0 for t in omft])
-    smin = np.array([t._singularity_handler._svd_s[5] / t._singularity_handler._svd_s[0] for t in omft])
-    np.savez(os.path.join(OUT, "config2_osc_nullspace.npz"), q=q, dq=dq, tau=tau, singular=singular, sigma_ratio=smin, x0=x0, R0=R0, **G)
+    tau, singular, smin, x0, R0, G = _osc_run("panda", N, q, dq, None, None, 32)
+    extra = {}
+    if SOURCE == "reference":
+        tau_e = _osc_run("panda", N, q, dq, None, None, 32, eigen_signs=True)[0]
+        extra = dict(tau_eigen_signs=tau_e, sign_sensitive=_sign_sensitive(tau, tau_e))
+    np.savez(os.path.join(OUT, "config2_osc_nullspace.npz"), q=q, dq=dq, tau=tau, singular=singular, sigma_ratio=smin, x0=x0, R0=R0,
+             source=source_tag(), **extra, **G)
 
 
 def config3():
@@ -83,14 +118,45 @@ def config3():
         t.parametrizeForceMotionSpaces(1, (0, 0, 1)); t.setGoalForce((0, 0, -5.0)); t.setClosedLoopForceControl(); t.enablePassivity()
     F = np.zeros((K, N, 3)); Mo = np.zeros((K, N, 3)); tau = np.zeros((K, N, 7)); rc = np.zeros((K, N))
     for k in range(K):
+        F[k], Mo[k] = sensed_ex09(N, k)
         for i in range(N):
-            g = rng_for(i * 100003 + k, stream=33)
-            F[k, i] = np.array([0, 0, -5.0]) + g.normal(0, 1.0, 3) * (3.0 if (k // 60) % 2 else 1.0)
-            Mo[k, i] = g.normal(0, 0.1, 3)
             omft[i].updateSensedForceAndMoment(F[k, i], Mo[k, i])
         tau[k] = ob.cycle()
         rc[k] = [t._POPC_force._Rc for t in omft]
-    np.savez(os.path.join(OUT, "config3_force_popc.npz"), q=q, dq=dq, tau0=tau0, sensed_force=F, sensed_moment=Mo, tau=tau, Rc=rc)
+    np.savez(os.path.join(OUT, "config3_force_popc.npz"), q=q, dq=dq, tau0=tau0, sensed_force=F, sensed_moment=Mo, tau=tau, Rc=rc, source=source_tag())
+
+
+CONFIG3_CHECK_CYCLES = (1, 50, 51, 250, 251, 300, 1000)
+
+
+def config3_1000():
+    """SURVEY.md 8(d) config 3 as written: the ex.09 set-up run for K = 1000 consecutive cycles (sensed wrench regenerated from
+    the seed by osc_testlib.sensed_ex09), torques kept at cycles {1, 50, 51, 250, 251, 300, 1000} plus every 100th, Rc at every
+    PC update; the state moves a little every cycle so that the model stage is re-evaluated"""
+    N, K = 8, 1000
+    dirs = [(1, 0, 0), (0, 1, 0), (0, 0, 1)]
+    q0, dq, _ = sample_states("panda", N, min_sigma_ratio=0.1, dirs=np.eye(6)[:, :3])
+    link, pt = TASK_POINTS["panda"]
+    ob = OracleBatch("panda", N); ob.set_state(q0, dq)
+    omft = ob.add_mft(link, (np.eye(3), np.array(pt)), dirs, []); ojt = ob.add_jt(); ob.finalize()
+    for t in omft:
+        t.parametrizeForceMotionSpaces(1, (0, 0, 1)); t.setGoalForce((0, 0, -5.0)); t.setClosedLoopForceControl(); t.enablePassivity()
+    keep = sorted(set(CONFIG3_CHECK_CYCLES) | set(range(100, K + 1, 100)))
+    tau = np.zeros((len(keep), N, 7)); rc = np.zeros((K // 50, N)); popc = None
+    q = q0.copy()
+    for k in range(1, K + 1):
+        F, Mo = sensed_ex09(N, k - 1)
+        for i in range(N):
+            omft[i].updateSensedForceAndMoment(F[i], Mo[i])
+        t = ob.cycle()
+        if k in keep:
+            tau[keep.index(k)] = t
+        if k % 50 == 0:
+            rc[k // 50 - 1] = [x._POPC_force._Rc for x in omft]
+        q = q0 + 0.05 * np.sin(2 * np.pi * k / 500.0) * dq      # bounded excursion around the sampled state
+        ob.set_state(q, dq)
+    popc = np.array([[x._POPC_force._passivity_observer_value, x._POPC_force._E_correction, x._POPC_force._Rc] for x in omft])
+    np.savez(os.path.join(OUT, "config3_force_popc_1000.npz"), q=q0, dq=dq, cycles=np.array(keep), tau=tau, Rc=rc, popc_final=popc, source=source_tag())
 
 
 def config4():
@@ -99,20 +165,71 @@ def config4():
     for name, dt_, dr_ in (("rrrr", [(1, 0, 0), (0, 1, 0)], [(0, 0, 1)]), ("puma_like", None, None)):
         N = 16
         q, dq, _ = sample_states(name, N)
-        link, pt = TASK_POINTS[name]
-        ob = OracleBatch(name, N); ob.set_state(q, dq)
-        omft = ob.add_mft(link, (np.eye(3), np.array(pt)), dt_, dr_); ojt = ob.add_jt(); ob.finalize()
+        tau, singular, smin, x0, R0, G = _osc_run(name, N, q, dq, dt_, dr_, 34)
+        extra = {}
+        if SOURCE == "reference":
+            tau_e = _osc_run(name, N, q, dq, dt_, dr_, 34, eigen_signs=True)[0]
+            extra = dict(tau_eigen_signs=tau_e, sign_sensitive=_sign_sensitive(tau, tau_e))
+        out.update({name + "_" + k: v for k, v in dict(q=q, dq=dq, tau=tau, singular=singular, **extra, **G).items()})
+    np.savez(os.path.join(OUT, "config4_mixed_dof.npz"), source=source_tag(), **out)
+
+
+def singular_replay_states(N=12):
+    """Panda states inside the blending band whose motion keeps them there for hundreds of cycles"""
+    q, dq, _ = sample_states("panda", 200)
+    from oracle.sai_model import SaiModel
+    from oracle.robots import make_chain
+    model = SaiModel(make_chain("panda"))
+    link, pt = TASK_POINTS["panda"]
+    pick = []
+    for i in range(200):
+        ok = True
+        for k in (0, 150, 300):
+            model.setQ(q[i] + 0.0002 * k * dq[i]); model.updateKinematics()
+            s = np.linalg.svd(model.J(link, pt), compute_uv=False)
+            ok = ok and (8e-3 < s[5] / s[0] < 5e-2)
+        if ok:
+            pick.append(i)
+        if len(pick) == N:
+            break
+    return q[pick], dq[pick]
+
+
+def config4_singular_replay():
+    """SingularityHandler.cpp:276-293 driven past its 200-entry history: 300 consecutive cycles inside the blending band, the state
+    drifting every cycle; torques of every cycle, the type counters and the history length at cycles 100/200/201/260/300"""
+    K = 300
+    q0, dq = singular_replay_states()
+    N = q0.shape[0]
+    link, pt = TASK_POINTS["panda"]
+    res = {}
+    for tag, eigen_signs in (("", False), ("_eigen_signs", True)):
+        if eigen_signs and SOURCE != "reference":
+            continue
+        ob = OracleBatch("panda", N, eigen_signs=eigen_signs); ob.set_state(q0, dq)
+        omft = ob.add_mft(link, (np.eye(3), np.array(pt))); ojt = ob.add_jt(); ob.finalize()
         x0 = np.array([t._current_position for t in omft]); R0 = np.array([t._current_orientation for t in omft])
-        G = goals_for(N, q.shape[1], x0, R0, q, 34)
+        G = goals_for(N, 7, x0, R0, q0, 35)
         apply_goals(omft, ojt, G)
-        tau = np.array([ob.cycle() for _ in range(3)])
-        singular = np.array([len(t._singularity_handler._singularity_types) != 0 for t in omft])
-        out.update({name + "_" + k: v for k, v in dict(q=q, dq=dq, tau=tau, singular=singular, **G).items()})
-    np.savez(os.path.join(OUT, "config4_mixed_dof.npz"), **out)
+        tau = np.zeros((K, N, 7)); counters = {}
+        for k in range(1, K + 1):
+            tau[k - 1] = ob.cycle()
+            if k in (100, 200, 201, 260, 300):
+                h = [t._singularity_handler for t in omft]
+                counters[k] = np.array([[x._type_1_counter, x._type_2_counter] for x in h])
+            ob.set_state(q0 + 0.0002 * k * dq, dq)
+        res["tau" + tag] = tau
+        res["counters" + tag] = np.array([counters[k] for k in (100, 200, 201, 260, 300)])
+        if not eigen_signs:
+            res.update(G)
+    np.savez_compressed(os.path.join(OUT, "config4_singular_replay.npz"), q=q0, dq=dq, counter_cycles=np.array([100, 200, 201, 260, 300]),
+                        source=source_tag(), **res)
 
 
 if __name__ == "__main__":
-    config1(); config2(); config3(); config4()
+    if "--source" in sys.argv:
+        SOURCE = sys.argv[sys.argv.index("--source") + 1]
+    config1(); config2(); config3(); config3_1000(); config4(); config4_singular_replay()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")

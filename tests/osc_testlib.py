@@ -71,6 +71,17 @@ def sample_states(robot_name, n_robots, min_sigma_ratio=None, dirs=None, first_i
     return q, dq, rejected
 
 
+def sensed_ex09(N, k):
+    """sensed wrench of cycle k (0-based) for the ex.09 closed-loop force scenario: goal force (0,0,-5) + noise whose level
+    alternates every 60 cycles so that the passivity controller engages and relaxes"""
+    F = np.zeros((N, 3)); Mo = np.zeros((N, 3))
+    for i in range(N):
+        g = rng_for(i * 100003 + k, stream=33)
+        F[i] = np.array([0, 0, -5.0]) + g.normal(0, 1.0, 3) * (3.0 if (k // 60) % 2 else 1.0)
+        Mo[i] = g.normal(0, 0.1, 3)
+    return F, Mo
+
+
 def rel_err(a, b):
     """per-robot max abs error relative to the robot's reference infinity norm"""
     a = np.asarray(a); b = np.asarray(b)

@@ -33,7 +33,7 @@ def test_cpp_matches_numpy_including_singular_branch(case, dec):
     n = q.shape[1]
     link, pt = TASK_POINTS[robot_name]
     comp = (np.eye(3), np.array(pt))
-    ob = OracleBatch(robot_name, N); ob.set_state(q, dq)
+    ob = OracleBatch(robot_name, N, kind="numpy"); ob.set_state(q, dq)
     omft = ob.add_mft(link, comp, dt_, dr_); ojt = ob.add_jt(); ob.finalize()
     cb = CppOracleBatch(robot_name, N); cb.set_state(q, dq)
     tm = cb.add_mft(link, comp, dt_, dr_); tj = cb.add_jt()
