@@ -13,9 +13,14 @@ robots are sharded by batch index, one process per GPU, no collective on the con
   e2e    the same metric through the C ABI with pinned HOST buffers: H2D of q, dq and D2H of tau inside
          the timed region;
   roofline  the fused kernel against the FP64 roofline (SURVEY.md 8d: 9.5 kFLOP per robot-cycle);
-  cpu_baseline  the C++ restatement of the reference path (oracle/cpp, kind "port": the reference itself
-         cannot be compiled here) looped over a bounded sample on the host cores.
---impl reference runs only that CPU arm.
+  cpu_baseline  the reference's own control law (oracle/_ref/libsai_ref.so: /root/reference/src compiled in place against
+         stand-ins for Eigen and sai-model, kind "reference") looped over a bounded sample on the host cores; the plain C++
+         port (oracle/cpp) is timed beside it (`port`), and takes over (kind "port") where the library was not built.
+--impl reference runs only that CPU arm, on the same 65,536 states as the GPU arm, all host threads.
+
+Timing: `--steps K` back-to-back cycles form one bracket (CUDA events, barrier + synchronize on both sides); brackets are
+repeated until at least MIN_TIMED_MS of device time and MIN_PASSES brackets have been taken, and the MEDIAN bracket is
+published (`ms_per_step` = median / K, `timing` lists the passes) -- a 20-step bracket alone lasts 0.7 ms.
 """
 import argparse
 import ctypes as C
@@ -36,9 +41,13 @@ METRIC = "robot_control_cycles_per_sec"
 UNIT = "cycles/s"
 FLOP_PER_CYCLE = 9.5e3
 FP64_PEAK_TFLOPS = 37.2       # 148 SM x 64 FMA/clk x 2 x 1.965 GHz (no FP64 entry in MEASURED_PEAKS.json)
+WORKLOAD = "config2: Panda MotionForceTask 6-DoF + JointTask null space via RobotController, OTG off, BIE decoupling (reference defaults)"
 ROBOT = "panda"
 LINK, POINT = "end-effector", (0.0, 0.0, 0.07)
 SEED = 1234
+MIN_TIMED_MS = 60.0           # device time over all brackets
+MIN_PASSES = 5
+LATENCY_SAMPLES = 1000        # >= 1000 single-cycle brackets for the percentiles
 
 
 def log(*a):
@@ -136,93 +145,163 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arm
-def run_cpu_baseline(n_sample, target_seconds, q, dq, goals, threads=None):
-    """C++ restatement of the reference path (setQ/setDq/updateModel + updateControllerTaskModels +
-    computeControlTorques per robot) on the host cores; returns cycles/s and a description."""
-    from oracle.cpp_ref import CppOracleBatch
-    cb = CppOracleBatch(ROBOT, n_sample)
-    threads = threads or cb.hardware_threads()
-    cb.set_state(q[:n_sample], dq[:n_sample])
-    tm = cb.add_mft(LINK, (np.eye(3), np.array(POINT)))
-    tj = cb.add_jt()
-    g = goals
-    cb.mft_set_goals(tm, g["xd"][:n_sample], g["Rd"][:n_sample], g["vd"][:n_sample], g["wd"][:n_sample], g["ad"][:n_sample], g["ald"][:n_sample])
-    cb.jt_set_goals(tj, g["qd"][:n_sample])
-    cb.step(q[:n_sample], dq[:n_sample], n_threads=threads)   # warm-up
-    times = []
-    t_start = time.time()
-    while True:
-        t0 = time.perf_counter()
-        cb.step(q[:n_sample], dq[:n_sample], n_threads=threads)
-        times.append(time.perf_counter() - t0)
-        if time.time() - t_start > target_seconds and len(times) >= 3:
-            break
-    med = float(np.median(times))
-    cb.close()
-    return n_sample / med, med, len(times), threads
+CPU_CHUNK = 8192      # robots per controller batch on the host (70 KB per reference controller instance)
 
 
-def oracle_goals_numpy(q, dq, rng):
-    """goal generation for the CPU-only arm: poses from the numpy oracle's kinematics"""
+class CpuControllers:
+    """A chunk of CPU controllers for config 2, all host threads: the reference's own compiled control law
+    (oracle/_ref/libsai_ref.so, kind "reference") when the library exists, else the C++ port (kind "port").
+    run(q, dq, goals) pushes any number of robots through it chunk by chunk: per robot and cycle setQ / setDq / updateModel,
+    goal setters, updateControllerTaskModels, computeControlTorques -- the reference's user loop."""
+
+    def __init__(self, kind, n_chunk):
+        self.kind, self.n_chunk = kind, n_chunk
+        comp = (np.eye(3), np.array(POINT))
+        if kind == "reference":
+            from oracle.sai_ref import RefBatch
+            self.b = RefBatch(ROBOT, n_chunk, oriented=False)
+            self.b.add_mft(LINK, comp); self.b.add_jt(); self.b.finalize()
+            self.tm, self.tj = 0, 1
+        else:
+            from oracle.cpp_ref import CppOracleBatch
+            self.b = CppOracleBatch(ROBOT, n_chunk)
+            self.tm = self.b.add_mft(LINK, comp); self.tj = self.b.add_jt()
+        self.threads = self.b.hardware_threads()
+
+    def run(self, q, dq, goals):
+        N = q.shape[0]
+        tau = np.zeros_like(q)
+        for lo in range(0, N, self.n_chunk):
+            hi = min(N, lo + self.n_chunk)
+            idx = np.arange(lo, lo + self.n_chunk) % N if hi - lo < self.n_chunk else slice(lo, hi)   # last chunk padded by wrapping
+            g = {k: v[idx] for k, v in goals.items()}
+            if self.kind == "reference":
+                self.b.mft_set_goals(self.tm, g["xd"], g["Rd"], g["vd"], g["wd"], g["ad"], g["ald"]); self.b.jt_set_goal_positions(self.tj, g["qd"])
+            else:
+                self.b.mft_set_goals(self.tm, g["xd"], g["Rd"], g["vd"], g["wd"], g["ad"], g["ald"]); self.b.jt_set_goals(self.tj, g["qd"])
+            t = self.b.step(q[idx], dq[idx], n_threads=self.threads)
+            tau[lo:hi] = t[:hi - lo]
+        return tau
+
+    def close(self):
+        self.b.close()
+
+
+def cpu_kind():
+    from oracle import sai_ref
+    return "reference" if sai_ref.available(oriented=False) else "port"
+
+
+KIND_TEXT = {"reference": "reference's own RobotController/MotionForceTask/JointTask sources compiled in place (oracle/_ref/libsai_ref.so; "
+                          "stand-ins for Eigen and sai-model), -O2",
+             "port": "C++ restatement of the reference path (oracle/cpp), -O2"}
+
+
+def run_cpu_baseline(n_sample, target_seconds, q, dq, goals):
+    """bounded sample of the GPU arm's own batch on the host cores; returns {kind: (cycles/s, seconds per run, runs, threads)}"""
+    out = {}
+    kinds = ["reference", "port"] if cpu_kind() == "reference" else ["port"]
+    g = {k: v[:n_sample] for k, v in goals.items()}
+    for kind in kinds:
+        cc = CpuControllers(kind, min(n_sample, CPU_CHUNK))
+        cc.run(q[:n_sample], dq[:n_sample], g)   # warm-up
+        times = []
+        t_start = time.time()
+        while True:
+            t0 = time.perf_counter()
+            cc.run(q[:n_sample], dq[:n_sample], g)
+            times.append(time.perf_counter() - t0)
+            if time.time() - t_start > target_seconds / len(kinds) and len(times) >= 3:
+                break
+        med = float(np.median(times))
+        out[kind] = (n_sample / med, med, len(times), cc.threads)
+        cc.close()
+    return out
+
+
+def sample_batch_cpu(n_robots, min_ratio, rng):
+    """the GPU arm's state distribution without a GPU: vectorised forward kinematics of the Panda in numpy for the
+    rejection test (input generation only)"""
     from oracle.robots import make_chain
-    from oracle.sai_model import SaiModel
-    m = SaiModel(make_chain(ROBOT))
-    N = q.shape[0]
-    x = np.zeros((N, 3)); R = np.zeros((N, 3, 3))
-    for i in range(N):
-        m.setQ(q[i]); m.updateKinematics()
-        x[i] = m.positionInWorld(LINK, POINT); R[i] = m.rotationInWorld(LINK)
-    return make_goals(rng, x, R, q)
+    ch = make_chain(ROBOT)
+    b, R_lb, t_lb = ch.link_frames[LINK]
+    p_local = t_lb + R_lb @ np.array(POINT)
+    q_ok = np.zeros((0, ch.n)); dq_ok = np.zeros((0, ch.n))
+    tried = 0
+    while q_ok.shape[0] < n_robots:
+        M = 65536
+        q = ch.q_lower + (0.1 + 0.8 * rng.random((M, ch.n))) * (ch.q_upper - ch.q_lower)
+        dq = rng.uniform(-1.0, 1.0, (M, ch.n))
+        R = np.tile(np.eye(3), (M, 1, 1)); p = np.zeros((M, 3))
+        axes, origins = [], []
+        for i in range(ch.n):
+            p = p + R @ ch.t_fix[i]
+            R = R @ ch.R_fix[i]
+            c, s_ = np.cos(q[:, i]), np.sin(q[:, i])
+            Rz = np.zeros((M, 3, 3)); Rz[:, 0, 0] = c; Rz[:, 0, 1] = -s_; Rz[:, 1, 0] = s_; Rz[:, 1, 1] = c; Rz[:, 2, 2] = 1
+            R = R @ Rz                    # every Panda joint is revolute about its local z axis
+            axes.append(R[:, :, 2].copy()); origins.append(p.copy())
+        x = p + R @ p_local
+        J = np.zeros((M, 6, ch.n))
+        for i in range(ch.n):
+            J[:, :3, i] = np.cross(axes[i], x - origins[i]); J[:, 3:, i] = axes[i]
+        w = np.linalg.eigvalsh(J @ J.transpose(0, 2, 1))
+        keep = np.sqrt(np.maximum(w[:, 0], 0) / w[:, -1]) >= min_ratio
+        q_ok = np.concatenate([q_ok, q[keep]]); dq_ok = np.concatenate([dq_ok, dq[keep]])
+        tried += M
+    return q_ok[:n_robots], dq_ok[:n_robots], 1.0 - q_ok.shape[0] / tried
 
 
 def reference_arm(args):
-    """bench.py --impl reference: the reference's own CPU path (C++ port, all host threads) on a bounded
-    sample of the same workload.  No GPU, no product code."""
+    """bench.py --impl reference: the reference's own CPU path on the same workload as the GPU arm (config 2, args.robots
+    robots per step, same state filter), all host threads.  No GPU, no product code."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.robots import make_chain
-    ch = make_chain(ROBOT)
-    n_sample = min(args.robots, 4096)
     rng = np.random.Generator(np.random.Philox(key=SEED))
-    # same state distribution as the GPU arm: non-singular branch only (s_min/s_max >= 0.1), by rejection
-    from oracle.sai_model import SaiModel
-    probe = SaiModel(ch)
-    qs, dqs = [], []
-    while len(qs) < n_sample:
-        qc = ch.q_lower + (0.1 + 0.8 * rng.random(ch.n)) * (ch.q_upper - ch.q_lower)
-        dqc = rng.uniform(-1.0, 1.0, ch.n)
-        probe.setQ(qc); probe.updateKinematics()
-        sv = np.linalg.svd(probe.J(LINK, POINT), compute_uv=False)
-        if sv[-1] / sv[0] >= 0.1:
-            qs.append(qc); dqs.append(dqc)
-    q, dq = np.array(qs), np.array(dqs)
-    goals = oracle_goals_numpy(q, dq, rng)
-    from oracle.cpp_ref import CppOracleBatch
-    cb = CppOracleBatch(ROBOT, n_sample)
-    threads = cb.hardware_threads()
-    cb.set_state(q, dq)
-    tm = cb.add_mft(LINK, (np.eye(3), np.array(POINT))); tj = cb.add_jt()
-    cb.mft_set_goals(tm, goals["xd"], goals["Rd"], goals["vd"], goals["wd"], goals["ad"], goals["ald"]); cb.jt_set_goals(tj, goals["qd"])
-    for _ in range(max(args.warmup, 1)):
-        cb.step(q, dq, n_threads=threads)
+    q, dq, rejected = sample_batch_cpu(args.robots, args.min_ratio, rng)
+    goals = goals_from_poses(q, rng)
+    kind = cpu_kind()
+    cc = CpuControllers(kind, min(args.robots, CPU_CHUNK))
+    for _ in range(max(1, min(args.warmup, 2))):
+        cc.run(q, dq, goals)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cb.step(q, dq, n_threads=threads)
+        tau = cc.run(q, dq, goals)
     dt = time.perf_counter() - t0
-    value = n_sample * args.steps / dt
-    sample = "%d robots x %d cycles per run (same state filter as the GPU arm: s_min/s_max >= 0.1)" \
-             ", C++ port of the reference path, %d host threads" % (n_sample, args.steps, threads)
+    if not np.isfinite(tau).all():
+        raise SystemExit("bench --impl reference: non-finite torques")
+    value = args.robots * args.steps / dt
+    sample = "%d robots x %d cycles (the GPU arm's config: same robot count per step, same state filter s_min/s_max >= %.3g), %s, %d host threads" \
+             % (args.robots, args.steps, args.min_ratio, KIND_TEXT[kind], cc.threads)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config2: Panda MotionForceTask 6-DoF + JointTask null space via RobotController, OTG off",
-                   "robots_per_step": n_sample, "note": "bounded sample of the GPU arm's workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "robots_per_gpu": args.robots, "robots_total": args.robots,
+                   "state_filter": "s_min/s_max >= %.3g, rejected fraction %.3f" % (args.min_ratio, rejected)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cc.threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
+
+
+def goals_from_poses(q, rng):
+    """current pose of every robot by vectorised forward kinematics (same arithmetic as sample_batch_cpu), then the
+    SURVEY 8d goal perturbation"""
+    from oracle.robots import make_chain
+    ch = make_chain(ROBOT)
+    b, R_lb, t_lb = ch.link_frames[LINK]
+    p_local = t_lb + R_lb @ np.array(POINT)
+    N = q.shape[0]
+    Rr = np.tile(np.eye(3), (N, 1, 1)); p = np.zeros((N, 3))
+    for i in range(ch.n):
+        p = p + Rr @ ch.t_fix[i]
+        Rr = Rr @ ch.R_fix[i]
+        c, s_ = np.cos(q[:, i]), np.sin(q[:, i])
+        Rz = np.zeros((N, 3, 3)); Rz[:, 0, 0] = c; Rz[:, 0, 1] = -s_; Rz[:, 1, 0] = s_; Rz[:, 1, 1] = c; Rz[:, 2, 2] = 1
+        Rr = Rr @ Rz
+    return make_goals(rng, p + Rr @ p_local, Rr @ R_lb, q)
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -300,20 +379,39 @@ def gpu_arm(args):
         clocks.start()
         time.sleep(0.25)
     t_wall0 = time.time()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for k in range(args.steps):     # the timed region: K back-to-back cycles, nothing else in the stream
-        step_device(sets[k % n_sets])
-    e1.record()
-    barrier()
+    # one bracket = args.steps back-to-back cycles, nothing else in the stream; brackets are repeated until MIN_TIMED_MS of
+    # device time and MIN_PASSES brackets are in, the median bracket is the published one
+    pass_ms = []
+    launches = 0
+    while True:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = sum(s["robot"].launchCount() for s in sets)
+        barrier()
+        e0.record()
+        for k in range(args.steps):     # the timed region: K back-to-back cycles, nothing else in the stream
+            step_device(sets[k % n_sets])
+        e1.record()
+        barrier()
+        pass_ms.append(e0.elapsed_time(e1))
+        launches = sum(s["robot"].launchCount() for s in sets) - l0
+        more = 1.0 if (len(pass_ms) < MIN_PASSES or (sum(pass_ms) < MIN_TIMED_MS and len(pass_ms) < 2000)) else 0.0
+        if world > 1:      # every rank takes the same number of brackets
+            flag = torch.tensor([more], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            more = float(flag.item())
+        if more == 0.0:
+            break
     t_wall1 = time.time()
-    total_ms = e0.elapsed_time(e1)
-    launches = sum(s["robot"].launchCount() for s in sets) - launches0
+    pass_ms = np.array(pass_ms)
+    if world > 1:          # bracket by bracket: the slowest rank
+        t = torch.tensor(pass_ms, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pass_ms = t.cpu().numpy()
+    total_ms = float(np.median(pass_ms))
     # latency of a single batched cycle, measured in a second pass: an event between two cycles keeps the next fast
     # kernel from being scheduled behind the general-path kernel (programmatic dependent launch), so the per-cycle
     # brackets are not part of the throughput measurement
-    lat_n = max(args.steps, 1000) if args.steps >= 100 else args.steps      # >= 1000 timed cycles for the percentiles
+    lat_n = max(args.steps, LATENCY_SAMPLES)      # >= 1000 timed cycles for the percentiles
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(lat_n)]
     for k in range(lat_n):
         ev[k][0].record()
@@ -344,8 +442,9 @@ def gpu_arm(args):
     for s_ in sets:
         s_["robot"].sync()
     barrier()
+    multi_steps = max(args.steps, 400)
     t0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(multi_steps):
         step_own_stream(sets[k % n_sets])
     for s_ in sets:
         s_["robot"].sync()
@@ -373,7 +472,7 @@ def gpu_arm(args):
         for s_ in sets:
             s_["robot"].sync()
 
-    e2e_steps = max(n_sets, min(args.steps, 200))
+    e2e_steps = 200
     for w in range(max(3, n_sets)):
         step_host(sets[w % n_sets])
     sync_all()
@@ -392,6 +491,25 @@ def gpu_arm(args):
     if not torch.equal(sets[0]["htau"], ref_tau):
         raise SystemExit("bench: end-to-end torques differ from the device-resident run")
 
+    # ---- what the host link gives: the same bytes per step (q, dq in, tau out) as plain pinned cudaMemcpyAsync copies with
+    # no kernel at all, host->device and device->host on two streams at once; the end-to-end number is bounded by it
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    d_in = torch.empty((2 * n, R), dtype=torch.float64, device=dev); d_out = torch.zeros((n, R), dtype=torch.float64, device=dev)
+    def copies(count):
+        for _ in range(count):
+            with torch.cuda.stream(s1):
+                d_in.copy_(sets[0]["hstate"], non_blocking=True)
+            with torch.cuda.stream(s2):
+                sets[0]["htau"].copy_(d_out, non_blocking=True)
+        s1.synchronize(); s2.synchronize()
+    copies(10)
+    barrier()
+    t0 = time.perf_counter()
+    copies(100)
+    link_ms = 1e3 * (time.perf_counter() - t0) / 100
+    barrier()
+    sets[0]["htau"].copy_(ref_tau)
+
     # ---- measured FP64 FMA rate of this GPU (rank 0): the datasheet-derived 37.2 TFLOP/s stays the roofline denominator,
     # the measured figure is reported next to it
     fp64_measured = None
@@ -403,9 +521,9 @@ def gpu_arm(args):
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, e2e_ms, multi_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_ms, multi_ms, link_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms, multi_ms = float(t[0]), float(t[1]), float(t[2])
+        e2e_ms, multi_ms, link_ms = float(t[0]), float(t[1]), float(t[2])
     value = world * R * args.steps / (total_ms * 1e-3)
     e2e_value = world * R * e2e_steps / (e2e_ms * 1e-3)
 
@@ -432,17 +550,24 @@ def gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config2: Panda MotionForceTask 6-DoF + JointTask null space via RobotController, OTG off, "
-                                   "BIE decoupling (reference defaults)",
+            "config": {"workload": WORKLOAD,
                        "robots_per_gpu": R, "robots_total": R * world,
                        "l2": "inputs larger than L2: %d controller instances (%.0f MB of state) used round-robin" % (n_sets, n_sets * R * 8 * 250 / 1e6),
                        "state_filter": "s_min/s_max >= %.3g, rejected fraction %.3f; robots on the general (SVD) path: %.4f" % (args.min_ratio, rejected, singular_fraction),
                        "parallelism": "robots sharded by batch index, %d process(es), no collective" % world},
+            "timing": {"brackets": int(pass_ms.size), "bracket_ms_median": total_ms, "bracket_ms_min": float(pass_ms.min()),
+                       "bracket_ms_max": float(pass_ms.max()), "timed_ms_total": float(pass_ms.sum()),
+                       "what": "each bracket = --steps back-to-back cycles between two CUDA events with barrier + synchronize on both sides; "
+                               "max over ranks per bracket; the median bracket is published"},
             "latency_ms": {"p50": float(np.percentile(per_step_ms, 50)), "p99": float(np.percentile(per_step_ms, 99)),
                            "max": float(per_step_ms.max()), "samples": int(per_step_ms.size), "what": "CUDA events around one batched cycle, rank 0"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * n * R * 8), "d2h_bytes_per_step": int(n * R * 8),
-                    "steps": e2e_steps, "passes_ms": [round(x, 3) for x in e2e_runs], "checksum": checksum},
-            "extra": {"device_resident_one_stream_per_instance": {"value": world * R * args.steps / (multi_ms * 1e-3), "unit": UNIT,
+                    "steps": e2e_steps, "passes_ms": [round(x, 3) for x in e2e_runs], "checksum": checksum,
+                    "host_link": {"ms_per_step_copies_only": link_ms, "gbs": (3 * n * R * 8) / (link_ms * 1e-3) / 1e9,
+                                  "e2e_fraction_of_link": link_ms / (e2e_ms / e2e_steps),
+                                  "what": "the same %d + %d bytes per step as plain pinned cudaMemcpyAsync host->device and device->host on two "
+                                          "streams at once, no kernel, max over ranks" % (2 * n * R * 8, n * R * 8)}},
+            "extra": {"device_resident_one_stream_per_instance": {"value": world * R * multi_steps / (multi_ms * 1e-3), "unit": UNIT,
                       "what": "same cycles, the %d controller instances on their own streams (independent batches overlap), host clock" % n_sets}},
             "gpu_launches": int(launches),
             "clocks": clk,
@@ -458,11 +583,15 @@ def gpu_arm(args):
         }
         # CPU baseline on rank 0 at N=1 only
         if world == 1 and not args.no_cpu:
-            n_sample = min(R, 4096)
-            v, med, reps, threads = run_cpu_baseline(n_sample, args.cpu_seconds, q, dq, goals)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                   "sample": "%d robots of the same batch x 1 cycle, median of %d runs (%.3f s each), C++ restatement of "
-                                             "the reference path incl. model update, -O2, %d host threads" % (n_sample, reps, med, threads)}
+            n_sample = min(R, 16384)
+            res = run_cpu_baseline(n_sample, args.cpu_seconds, q, dq, goals)
+            kind = "reference" if "reference" in res else "port"
+            v, med, reps, threads = res[kind]
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                                   "sample": "%d robots of the same batch x 1 cycle, median of %d runs (%.3f s each), %s, incl. the model update, "
+                                             "%d host threads" % (n_sample, reps, med, KIND_TEXT[kind], threads)}
+            if kind == "reference":
+                out["cpu_baseline"]["port"] = {"value": res["port"][0], "what": KIND_TEXT["port"] + ", same sample and threads"}
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out), flush=True)
@@ -478,7 +607,7 @@ def main():
     ap.add_argument("--robots", type=int, default=65536, help="robots per GPU (BASELINE config 2: 65,536)")
     ap.add_argument("--sets", type=int, default=8, help="controller instances used round-robin (working set > L2)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--cpu-seconds", type=float, default=16.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--min-ratio", type=float, default=0.1, help="reject states with s_min/s_max below this (0: unfiltered, about half of the Panda states then take the singular branch)")
     args = ap.parse_args()

@@ -111,6 +111,11 @@ public:
 	const TaskType& getTaskType() const { return _task_type; }
 	const std::string& getTaskName() const { return _task_name; }
 	int id() const { return _id; }
+	// TemplateTask.h:74,82,89: n x n row-major per robot, SoA out (component r * n + c of robot i at soa[(r * n + c) * N + i]);
+	// evaluated from the robot's current state (what updateControllerTaskModels() yields there)
+	void getTaskNullspace(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_TASK_NULLSPACE, soa, w); }
+	void getPreviousTasksNullspace(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_TASK_PREVIOUS_NULLSPACE, soa, w); }
+	void getTaskAndPreviousNullspace(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_TASK_AND_PREVIOUS_NULLSPACE, soa, w); }
 
 protected:
 	osc_handle* h() const { return _robot->handle(); }
@@ -267,6 +272,13 @@ public:
 	void getSensedForceControlWorldFrame(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_SENSED_FORCE_CONTROL_WORLD, soa, w); }
 	void getSensedMomentControlWorldFrame(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_SENSED_MOMENT_CONTROL_WORLD, soa, w); }
 	void getUnitMassForce(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_UNIT_MASS_FORCE, soa, w); }
+	// MotionForceTask.h:268-269, :613-616
+	void getPositionError(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_POSITION_ERROR, soa, w); }
+	void getOrientationError(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_ORIENTATION_ERROR, soa, w); }
+	void sigmaForce(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_SIGMA_FORCE, soa, w); }
+	void sigmaPosition(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_SIGMA_POSITION, soa, w); }
+	void sigmaMoment(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_SIGMA_MOMENT, soa, w); }
+	void sigmaOrientation(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_SIGMA_ORIENTATION, soa, w); }
 
 	// ---- gains and options
 	void setPosControlGains(double kp, double kv, double ki = 0) { setPosControlGains(Vec3{kp, kp, kp}, Vec3{kv, kv, kv}, Vec3{ki, ki, ki}); }

@@ -164,11 +164,26 @@ typedef enum {
 	OSC_MFT_INTEGRATED_MOMENT_ERROR = 18,	  /* (3) */
 	OSC_MFT_POPC_STATE = 19,				  /* (4) passivity observer, E_correction, Rc, sum vcl^2 */
 	OSC_MFT_TYPE1_POSTURE = 20,				  /* (n) SingularityHandler::setType1Posture / _q_prior */
+	/* computed on request from the state the last osc_compute_control_torques left (read only):
+	 * MotionForceTask::getPositionError / getOrientationError (MotionForceTask.cpp:540-546, MotionForceTask.h:268-269),
+	 * sigmaForce / sigmaPosition / sigmaMoment / sigmaOrientation (MotionForceTask.cpp:892-971, MotionForceTask.h:613-616) */
+	OSC_MFT_POSITION_ERROR = 21,	 /* (3) */
+	OSC_MFT_ORIENTATION_ERROR = 22,	 /* (3) */
+	OSC_MFT_SIGMA_FORCE = 23,		 /* (9) row-major */
+	OSC_MFT_SIGMA_POSITION = 24,	 /* (9) */
+	OSC_MFT_SIGMA_MOMENT = 25,		 /* (9) */
+	OSC_MFT_SIGMA_ORIENTATION = 26,	 /* (9) */
 	/* JointTask: JointTask.h:140-182 */
 	OSC_JT_GOAL_POSITION = 32,		 /* (k) */
 	OSC_JT_GOAL_VELOCITY = 33,		 /* (k) */
 	OSC_JT_GOAL_ACCELERATION = 34,	 /* (k) */
-	OSC_JT_INTEGRATED_POSITION_ERROR = 35 /* (k) */
+	OSC_JT_INTEGRATED_POSITION_ERROR = 35, /* (k) */
+	/* any task: TemplateTask::getTaskNullspace / getPreviousTasksNullspace / getTaskAndPreviousNullspace
+	 * (TemplateTask.h:74,82,89; JointTask.h:222-226, MotionForceTask.h:205-209), n x n row-major per robot, read only.
+	 * Evaluated on request from the handle's current state: what updateControllerTaskModels() yields at that state. */
+	OSC_TASK_NULLSPACE = 48,				/* (n*n) */
+	OSC_TASK_PREVIOUS_NULLSPACE = 49,		/* (n*n) */
+	OSC_TASK_AND_PREVIOUS_NULLSPACE = 50	/* (n*n) */
 } osc_field;
 
 typedef struct osc_handle osc_handle;
@@ -278,6 +293,15 @@ int osc_step(osc_handle* h, const double* q, const double* dq, double* tau_out, 
  * tau_out unread) until osc_sync(h) returns; lets a caller pipeline the host<->device copies of several handles */
 int osc_step_async(osc_handle* h, const double* q, const double* dq, double* tau_out, int mem_kind);
 int osc_get_status(osc_handle* h, uint32_t* flags_out, int mem_kind);
+/* Per-cycle observers of MotionForceTask that the torques do not need: getCurrentLinearVelocity / getCurrentAngularVelocity /
+ * getUnitMassForce (MotionForceTask.h:121-129, :266) and the orientation error behind getOrientationError.  The reference
+ * refreshes them in every computeTorques (MotionForceTask.cpp:291-298, :478); so does this library by default (enabled = 1).
+ * With enabled = 0 the cycle kernels skip the 15 stores per robot and reading those fields returns OSC_ERR_STATE. */
+int osc_enable_observers(osc_handle* h, int enabled);
+/* Contiguous shard of a batch: robots [*first, *first + *count) of n_robots belong to shard `rank` of
+ * `world` (robot i -> shard floor(i * world / n_robots)).  One handle per device is created with *count robots; no call of
+ * this library ever exchanges data between handles. */
+int osc_shard_range(int64_t n_robots, int rank, int world, int64_t* first, int64_t* count);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t osc_launch_count(const osc_handle* h);
 

@@ -517,6 +517,38 @@ int sref_call(void* h, int task, int robot, const char* method, const double* in
 	SREF_CATCH(b, -1)
 }
 
+// bulk goal setters for the timed CPU arms (bench.py): g [n_robots][24] = position 3, orientation 9 (row-major), linear and
+// angular velocity 3 + 3, linear and angular acceleration 3 + 3; joint goal positions [n_robots][k]
+int sref_mft_set_goals(void* h, int task, const double* g) {
+	RefBatch* b = (RefBatch*)h;
+	SREF_TRY
+	for (size_t i = 0; i < b->robots.size(); i++) {
+		auto* t = static_cast<MotionForceTask*>(b->robots[i].tasks.at(task).get());
+		const double* p = g + 24 * i;
+		t->setGoalPosition(rowv3(p));
+		t->setGoalOrientation(rowm3(p + 3));
+		t->setGoalLinearVelocity(rowv3(p + 12));
+		t->setGoalAngularVelocity(rowv3(p + 15));
+		t->setGoalLinearAcceleration(rowv3(p + 18));
+		t->setGoalAngularAcceleration(rowv3(p + 21));
+	}
+	return 0;
+	SREF_CATCH(b, -1)
+}
+int sref_jt_set_goal_positions(void* h, int task, const double* pos) {
+	RefBatch* b = (RefBatch*)h;
+	SREF_TRY
+	for (size_t i = 0; i < b->robots.size(); i++) {
+		auto* t = static_cast<JointTask*>(b->robots[i].tasks.at(task).get());
+		const int k = t->getTaskDof();
+		VectorXd v(k);
+		for (int j = 0; j < k; j++) v(j) = pos[(size_t)k * i + j];
+		t->setGoalPosition(v);
+	}
+	return 0;
+	SREF_CATCH(b, -1)
+}
+
 // one control cycle for every robot: tau [n_robots][n]
 int sref_cycle(void* h, double* tau, int use_prev, int n_threads) {
 	RefBatch* b = (RefBatch*)h;

@@ -276,5 +276,13 @@ class RefBatch:
         self._check(self.lib.sref_step(self.h, _p(q), _p(dq), _p(tau), C.c_int(int(use_prev)), C.c_int(n_threads)))
         return tau
 
+    def mft_set_goals(self, task_index, pos, ori, v, w, a, al):
+        g = np.ascontiguousarray(np.concatenate([_c(pos), _c(ori).reshape(self.N, 9), _c(v), _c(w), _c(a), _c(al)], axis=1))
+        self._check(self.lib.sref_mft_set_goals(self.h, C.c_int(task_index), _p(g)))
+
+    def jt_set_goal_positions(self, task_index, pos):
+        pos = _c(pos)
+        self._check(self.lib.sref_jt_set_goal_positions(self.h, C.c_int(task_index), _p(pos)))
+
     def hardware_threads(self):
         return int(self.lib.sref_hardware_threads())

@@ -154,6 +154,10 @@ class BatchedRobot:
     def sync(self):
         _check(self.handle, self._lib.osc_sync(self.handle))
 
+    def enableObservers(self, flag=True):
+        """osc_enable_observers: per-cycle refresh of getCurrentLinearVelocity / AngularVelocity / getUnitMassForce (default on)"""
+        _check(self.handle, self._lib.osc_enable_observers(self.handle, 1 if flag else 0))
+
     def setStream(self, cuda_stream_ptr):
         _check(self.handle, self._lib.osc_set_stream(self.handle, C.c_void_p(cuda_stream_ptr)))
 
@@ -233,6 +237,15 @@ class _Task:
 
     def reInitializeTask(self):
         _check(self._robot.handle, self._lib.osc_reinitialize_task(self._robot.handle, self.task_id))
+
+    # TemplateTask.h:74,82,89 -- [N, n, n], evaluated from the robot's current state
+    def _nullspace(self, field):
+        n = self._robot.dof()
+        return self._get(field).reshape(-1, n, n)
+
+    def getTaskNullspace(self): return self._nullspace(capi.TASK_NULLSPACE)
+    def getPreviousTasksNullspace(self): return self._nullspace(capi.TASK_PREVIOUS_NULLSPACE)
+    def getTaskAndPreviousNullspace(self): return self._nullspace(capi.TASK_AND_PREVIOUS_NULLSPACE)
 
 
 class JointTask(_Task):
@@ -385,6 +398,13 @@ class MotionForceTask(_Task):
     def getSensedForceControlWorldFrame(self): return self._get(capi.MFT_SENSED_FORCE_CONTROL_WORLD)
     def getSensedMomentControlWorldFrame(self): return self._get(capi.MFT_SENSED_MOMENT_CONTROL_WORLD)
     def getUnitMassForce(self): return self._get(capi.MFT_UNIT_MASS_FORCE)
+    # MotionForceTask.h:268-269, :613-616
+    def getPositionError(self): return self._get(capi.MFT_POSITION_ERROR)
+    def getOrientationError(self): return self._get(capi.MFT_ORIENTATION_ERROR)
+    def sigmaForce(self): return self._get(capi.MFT_SIGMA_FORCE).reshape(-1, 3, 3)
+    def sigmaPosition(self): return self._get(capi.MFT_SIGMA_POSITION).reshape(-1, 3, 3)
+    def sigmaMoment(self): return self._get(capi.MFT_SIGMA_MOMENT).reshape(-1, 3, 3)
+    def sigmaOrientation(self): return self._get(capi.MFT_SIGMA_ORIENTATION).reshape(-1, 3, 3)
 
     @staticmethod
     def _g3(kp, kv, ki, what):

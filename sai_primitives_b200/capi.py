@@ -66,10 +66,19 @@ MFT_INTEGRATED_FORCE_ERROR = 17
 MFT_INTEGRATED_MOMENT_ERROR = 18
 MFT_POPC_STATE = 19
 MFT_TYPE1_POSTURE = 20
+MFT_POSITION_ERROR = 21
+MFT_ORIENTATION_ERROR = 22
+MFT_SIGMA_FORCE = 23
+MFT_SIGMA_POSITION = 24
+MFT_SIGMA_MOMENT = 25
+MFT_SIGMA_ORIENTATION = 26
 JT_GOAL_POSITION = 32
 JT_GOAL_VELOCITY = 33
 JT_GOAL_ACCELERATION = 34
 JT_INTEGRATED_POSITION_ERROR = 35
+TASK_NULLSPACE = 48
+TASK_PREVIOUS_NULLSPACE = 49
+TASK_AND_PREVIOUS_NULLSPACE = 50
 
 D = C.c_double
 I32 = C.c_int32
@@ -175,6 +184,8 @@ SYMBOLS = {
     "osc_step_async": (C.c_int, [_H, _PD, _PD, _PD, C.c_int]),
     "osc_get_status": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "osc_launch_count": (C.c_int64, [_H]),
+    "osc_enable_observers": (C.c_int, [_H, C.c_int]),
+    "osc_shard_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "osc_urdf_register": (C.c_int, [C.c_char_p, C.c_char_p]),
     "osc_urdf_register_file": (C.c_int, [C.c_char_p, C.c_char_p]),
     "osc_urdf_last_error": (C.c_char_p, []),

@@ -1,4 +1,5 @@
 #include "osc_aux_kernels.cuh"
+#include "osc_observers.cuh"
 #include "osc_launch.h"
 
 namespace osc {
@@ -72,6 +73,10 @@ cudaError_t launch_jla(const OscProgram& P, cudaStream_t stream) {
 	jp.max_torque_ratio_pos_limit = 1.0;
 	jp.max_torque_ratio_vel_limit = 0.05;
 	DISPATCH_N(P.model.n, (jla_kernel<N_><<<grid_for(P.n_robots, 128), 128, 0, stream>>>(P, jp)));
+	return cudaGetLastError();
+}
+cudaError_t launch_observer(const OscProgram& P, int task, int kind, double* out, cudaStream_t stream) {
+	DISPATCH_N(P.model.n, (osc_observer_kernel<N_><<<grid_for(P.n_robots, 64), 64, 0, stream>>>(P, task, kind, out)));
 	return cudaGetLastError();
 }
 cudaError_t launch_reinit_jt(const OscProgram& P, int jt_index, cudaStream_t stream) {

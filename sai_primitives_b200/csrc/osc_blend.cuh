@@ -780,6 +780,7 @@ __global__ void __launch_bounds__(64) osc_blend_kernel(const __grid_constant__ O
 		const int64_t i = (int64_t)P.sing_list[slot];
 		if (!blend_robot<N, HAS_JT>(P, i)) generic_cycle_one<N>(P, i, OSC_STATUS_SINGULAR_PATH);
 	}
+	publish_general_done(P, count);
 }
 
 }  // namespace osc

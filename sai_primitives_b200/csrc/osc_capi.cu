@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -45,6 +46,13 @@ struct osc_handle {
 	uint32_t* d_status = nullptr;
 	double *d_fs = nullptr, *d_ms = nullptr;  // staging for sensed wrench (3 x N each)
 	int32_t *d_sing_list = nullptr, *d_sing_count = nullptr;
+	// cycle pipelining (osc_pipeline.cuh): per-block cycle numbers, general-path completion word, mapped host word
+	uint32_t *d_block_epoch = nullptr, *d_general_done = nullptr;
+	double* d_sim = nullptr;	  // staging of osc_sim_integrate with host buffers (q, dq, tau)
+	double* d_scratch = nullptr;  // output of the on-request observers (osc_observers.cuh)
+	size_t scratch_doubles = 0;
+	int32_t* h_seen = nullptr;	// mapped pinned: hand-over count of the last completed cycle
+	int clean_cycles = 0;
 	std::vector<void*> allocations;
 	std::string err;
 	int64_t launches = 0;
@@ -251,14 +259,28 @@ struct FieldInfo {
 	int comp;
 	int ncomp;
 	bool writable;
+	int observer = -1;		  // >= 0: osc::ObserverKind evaluated on request (osc_observers.cuh), comp unused
+	bool needs_observers = false;  // refreshed by the cycle kernels only while osc_enable_observers is on
 };
 
 bool field_info(const osc_handle* h, int task_id, int field, FieldInfo& fi) {
 	if (task_id < 0 || task_id >= (int)h->tasks.size()) return false;
 	const TaskInfo& t = h->tasks[task_id];
 	const int n = h->model.n;
+	switch (field) {
+		case OSC_TASK_NULLSPACE: fi = {t.type, 0, n * n, false, 0}; return true;
+		case OSC_TASK_PREVIOUS_NULLSPACE: fi = {t.type, 0, n * n, false, 1}; return true;
+		case OSC_TASK_AND_PREVIOUS_NULLSPACE: fi = {t.type, 0, n * n, false, 2}; return true;
+		default: break;
+	}
 	if (t.type == OSC_TASK_MOTION_FORCE) {
 		switch (field) {
+			case OSC_MFT_POSITION_ERROR: fi = {t.type, 0, 3, false, 3}; return true;
+			case OSC_MFT_ORIENTATION_ERROR: fi = {t.type, 0, 3, false, 4, true}; return true;
+			case OSC_MFT_SIGMA_FORCE: fi = {t.type, 0, 9, false, 5}; return true;
+			case OSC_MFT_SIGMA_POSITION: fi = {t.type, 0, 9, false, 6}; return true;
+			case OSC_MFT_SIGMA_MOMENT: fi = {t.type, 0, 9, false, 7}; return true;
+			case OSC_MFT_SIGMA_ORIENTATION: fi = {t.type, 0, 9, false, 8}; return true;
 			case OSC_MFT_GOAL_POSITION: fi = {t.type, MC_GOAL_POS, 3, true}; return true;
 			case OSC_MFT_GOAL_ORIENTATION: fi = {t.type, MC_GOAL_ORI, 9, true}; return true;
 			case OSC_MFT_GOAL_LINEAR_VELOCITY: fi = {t.type, MC_GOAL_LINVEL, 3, true}; return true;
@@ -269,11 +291,11 @@ bool field_info(const osc_handle* h, int task_id, int field, FieldInfo& fi) {
 			case OSC_MFT_GOAL_MOMENT: fi = {t.type, MC_GOAL_MOMENT, 3, true}; return true;
 			case OSC_MFT_CURRENT_POSITION: fi = {t.type, MC_CUR_POS, 3, false}; return true;
 			case OSC_MFT_CURRENT_ORIENTATION: fi = {t.type, MC_CUR_ORI, 9, false}; return true;
-			case OSC_MFT_CURRENT_LINEAR_VELOCITY: fi = {t.type, MC_CUR_LINVEL, 3, false}; return true;
-			case OSC_MFT_CURRENT_ANGULAR_VELOCITY: fi = {t.type, MC_CUR_ANGVEL, 3, false}; return true;
+			case OSC_MFT_CURRENT_LINEAR_VELOCITY: fi = {t.type, MC_CUR_LINVEL, 3, false, -1, true}; return true;
+			case OSC_MFT_CURRENT_ANGULAR_VELOCITY: fi = {t.type, MC_CUR_ANGVEL, 3, false, -1, true}; return true;
 			case OSC_MFT_SENSED_FORCE_CONTROL_WORLD: fi = {t.type, MC_SENSED_F, 3, false}; return true;
 			case OSC_MFT_SENSED_MOMENT_CONTROL_WORLD: fi = {t.type, MC_SENSED_M, 3, false}; return true;
-			case OSC_MFT_UNIT_MASS_FORCE: fi = {t.type, MC_UNIT_MASS_FORCE, 6, false}; return true;
+			case OSC_MFT_UNIT_MASS_FORCE: fi = {t.type, MC_UNIT_MASS_FORCE, 6, false, -1, true}; return true;
 			case OSC_MFT_INTEGRATED_POSITION_ERROR: fi = {t.type, MC_INT_POS, 3, false}; return true;
 			case OSC_MFT_INTEGRATED_ORIENTATION_ERROR: fi = {t.type, MC_INT_ORI, 3, false}; return true;
 			case OSC_MFT_INTEGRATED_FORCE_ERROR: fi = {t.type, MC_INT_FORCE, 3, false}; return true;
@@ -364,6 +386,22 @@ int osc_create(const osc_model_desc* model, int64_t n_robots, int device, osc_ha
 	h->prog.sing_list = h->d_sing_list;
 	h->prog.sing_count = h->d_sing_count;
 	h->prog.sing_parity = 0;
+	// SAI_B200_NO_PIPELINE=1 (measurements only): every cycle waits for the whole previous grid, as before
+	const char* nopipe = getenv("SAI_B200_NO_PIPELINE");
+	if (!(nopipe && nopipe[0] == '1')) {
+		const size_t blocks = ((size_t)n_robots + osc::kCycleBlock - 1) / osc::kCycleBlock;
+		if ((rc = dev_alloc(h, &h->d_block_epoch, blocks, true)) != OSC_OK) return cleanup(rc);
+		if ((rc = dev_alloc(h, &h->d_general_done, (size_t)2, true)) != OSC_OK) return cleanup(rc);
+		if (cudaHostAlloc((void**)&h->h_seen, sizeof(int32_t), cudaHostAllocMapped) != cudaSuccess) return cleanup(fail(h, OSC_ERR_CUDA, "cudaHostAlloc failed"));
+		*h->h_seen = -1;  // nothing observed yet
+		int32_t* d_seen = nullptr;
+		if (cudaHostGetDevicePointer((void**)&d_seen, h->h_seen, 0) != cudaSuccess) return cleanup(fail(h, OSC_ERR_CUDA, "cudaHostGetDevicePointer failed"));
+		h->prog.block_epoch = h->d_block_epoch;
+		h->prog.general_done = h->d_general_done;
+		h->prog.host_seen = d_seen;
+	}
+	h->prog.epoch = 0;
+	h->prog.write_observers = 1;  // like the reference: every computeTorques refreshes the observers
 	*out = h;
 	return OSC_OK;
 }
@@ -372,7 +410,9 @@ int osc_destroy(osc_handle* h) {
 	if (!h) return OSC_OK;
 	cudaSetDevice(h->device);
 	if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+	if (h->stream && h->stream != h->own_stream) cudaStreamSynchronize(h->stream);
 	for (void* p : h->allocations) cudaFree(p);
+	if (h->h_seen) cudaFreeHost(h->h_seen);
 	if (h->own_stream) cudaStreamDestroy(h->own_stream);
 	delete h;
 	return OSC_OK;
@@ -931,8 +971,23 @@ int osc_get_field(osc_handle* h, int task_id, int field, double* out, int mem_ki
 	FieldInfo fi;
 	if (!field_info(h, task_id, field, fi)) return fail(h, OSC_ERR_INVALID_ARGUMENT, "unknown field for this task");
 	if (!out) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null output");
+	if (fi.needs_observers && !h->prog.write_observers)
+		return fail(h, OSC_ERR_STATE, "this field is refreshed by the cycle kernels only while osc_enable_observers(h, 1) is in effect");
 	const double* src = task_state(h, task_id) + (size_t)fi.comp * h->NR;
 	const size_t bytes = (size_t)fi.ncomp * h->NR * sizeof(double);
+	if (fi.observer >= 0) {
+		if (!h->finalized) return fail(h, OSC_ERR_STATE, "controller not finalized");
+		if (h->scratch_doubles < (size_t)fi.ncomp * h->NR) {
+			double* p = nullptr;
+			int rc = dev_alloc(h, &p, (size_t)OSC_MAX_DOF * OSC_MAX_DOF * h->NR, false);
+			if (rc != OSC_OK) return rc;
+			h->d_scratch = p;
+			h->scratch_doubles = (size_t)OSC_MAX_DOF * OSC_MAX_DOF * h->NR;
+		}
+		CUDA_TRY(h, osc::launch_observer(h->prog, task_id, fi.observer, h->d_scratch, h->stream));
+		h->launches++;
+		src = h->d_scratch;
+	}
 	if (mem_kind == OSC_MEM_HOST) {
 		CUDA_TRY(h, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, h->stream));
 		CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -975,6 +1030,21 @@ int osc_enable_joint_limit_avoidance(osc_handle* h, int enabled) {
 	return OSC_OK;
 }
 
+int osc_enable_observers(osc_handle* h, int enabled) {
+	ENTER(h);
+	h->prog.write_observers = enabled ? 1 : 0;
+	return OSC_OK;
+}
+
+int osc_shard_range(int64_t n_robots, int rank, int world, int64_t* first, int64_t* count) {
+	if (n_robots < 0 || world <= 0 || rank < 0 || rank >= world || !first || !count) return OSC_ERR_INVALID_ARGUMENT;
+	// robot i belongs to shard floor(i * world / n_robots): shard r starts at ceil(r * n_robots / world)
+	const int64_t lo = (rank * n_robots + world - 1) / world, hi = ((rank + 1) * n_robots + world - 1) / world;
+	*first = lo;
+	*count = hi - lo;
+	return OSC_OK;
+}
+
 int osc_update_task_models(osc_handle* h) {
 	ENTER(h);
 	if (!h->finalized) return fail(h, OSC_ERR_STATE, "controller not finalized");
@@ -989,6 +1059,14 @@ static int run_cycle(osc_handle* h, double* tau_out, int mem_kind, bool sync_hos
 	h->prog.tau = (mem_kind == OSC_MEM_DEVICE) ? tau_out : h->d_tau;
 	h->prog.update_models = h->models_armed ? 1 : 0;
 	h->models_armed = false;
+	h->prog.epoch += 1;
+	// scheduling hint only (any grid size is correct): after a few cycles without hand-overs a handful of general-path blocks
+	// is launched instead of a grid that covers the machine
+	if (h->h_seen) {
+		const int32_t seen = *(volatile int32_t*)h->h_seen;
+		h->clean_cycles = (seen == 0) ? h->clean_cycles + 1 : 0;
+		h->prog.general_grid_small = h->clean_cycles >= 4 ? 1 : 0;
+	}
 	cudaError_t e;
 	if (h->jla_enabled) {
 		// RobotController.cpp:96-116: the avoidance blend comes after the task torques (and their saturation) and before
@@ -1088,11 +1166,19 @@ int osc_sim_integrate(osc_handle* h, double* q, double* dq, const double* tau, d
 	if (mem_kind == OSC_MEM_DEVICE) {
 		CUDA_TRY(h, osc::launch_sim_integrate(h->prog, q, dq, tau, dt, substeps, h->stream));
 	} else if (mem_kind == OSC_MEM_HOST) {
-		CUDA_TRY(h, h2d_state(h, q, dq));
-		CUDA_TRY(h, cudaMemcpyAsync(h->d_tau, tau, bytes, cudaMemcpyHostToDevice, h->stream));
-		CUDA_TRY(h, osc::launch_sim_integrate(h->prog, h->d_q, h->d_dq, h->d_tau, dt, substeps, h->stream));
-		CUDA_TRY(h, cudaMemcpyAsync(q, h->d_q, bytes, cudaMemcpyDeviceToHost, h->stream));
-		CUDA_TRY(h, cudaMemcpyAsync(dq, h->d_dq, bytes, cudaMemcpyDeviceToHost, h->stream));
+		// the simulation has its own staging buffers: the controller's state (osc_set_state) and its last torques are separate
+		// objects in the reference too (sai-simulation vs SaiModel) and must survive this call
+		if (!h->d_sim) {
+			int rc = dev_alloc(h, &h->d_sim, 3 * (size_t)h->model.n * h->NR, false);
+			if (rc != OSC_OK) return rc;
+		}
+		double *sq = h->d_sim, *sdq = h->d_sim + (size_t)h->model.n * h->NR, *stau = h->d_sim + 2 * (size_t)h->model.n * h->NR;
+		CUDA_TRY(h, cudaMemcpyAsync(sq, q, bytes, cudaMemcpyHostToDevice, h->stream));
+		CUDA_TRY(h, cudaMemcpyAsync(sdq, dq, bytes, cudaMemcpyHostToDevice, h->stream));
+		CUDA_TRY(h, cudaMemcpyAsync(stau, tau, bytes, cudaMemcpyHostToDevice, h->stream));
+		CUDA_TRY(h, osc::launch_sim_integrate(h->prog, sq, sdq, stau, dt, substeps, h->stream));
+		CUDA_TRY(h, cudaMemcpyAsync(q, sq, bytes, cudaMemcpyDeviceToHost, h->stream));
+		CUDA_TRY(h, cudaMemcpyAsync(dq, sdq, bytes, cudaMemcpyDeviceToHost, h->stream));
 		CUDA_TRY(h, cudaStreamSynchronize(h->stream));
 	} else {
 		return fail(h, OSC_ERR_INVALID_ARGUMENT, "bad mem_kind");

@@ -29,6 +29,7 @@
 #pragma once
 #include "osc_kindyn.cuh"
 #include "osc_launch.h"
+#include "osc_pipeline.cuh"
 #include "osc_tasks.cuh"
 
 namespace osc {
@@ -109,6 +110,7 @@ struct IndexType<true> {
 #endif
 
 DEVI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 
 // y = B^T v: the six world-frame components of a task vector reduced to the R coordinates of the task range
 // (identity for a full task)
@@ -218,8 +220,9 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 #ifndef OSC_NO_PREFETCH
 	prefetch_block_rows<N, R, HAS_JT>(P, blockIdx.x);
 #endif
-	asm volatile("griddepcontrol.wait;" ::: "memory");
-	if (i_raw == 0 && P.sing_count) P.sing_count[P.sing_parity ^ 1] = 0;
+	wait_previous_cycle(P);
+	if (!P.block_epoch && i_raw == 0 && P.sing_count) P.sing_count[P.sing_parity ^ 1] = 0;
+	bool handed_over = false;
 	double q[N];
 #pragma unroll
 	for (int j = 0; j < N; j++) q[j] = P.q[(IDX)j * NR + i];
@@ -410,10 +413,16 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				const int lane = threadIdx.x & 31;
 				const int leader = __ffs(m) - 1;
 				int base = 0;
-				if (lane == leader) base = atomicAdd(&P.sing_count[P.sing_parity], __popc(m));
+				if (lane == leader) {
+					// the list of this parity was last read by the general-path kernel two cycles ago
+					if (P.general_done)
+						while ((int32_t)(ld_acquire_u32(P.general_done) - (P.epoch - 2u)) < 0) __nanosleep(256);
+					base = atomicAdd(&P.sing_count[P.sing_parity], __popc(m));
+				}
 				base = __shfl_sync(m, base, leader);
 				P.sing_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
 				alive = false;	// the general-path kernel owns this robot from here on
+				handed_over = true;
 			}
 		}
 		// classifySingularity with an empty singular range clears the handler memory (:239-245); only robots that
@@ -759,6 +768,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		for (int j = 0; j < N; j++) P.tau[(IDX)j * NR + i] = tau[j];
 		P.status[i] = status;
 	}
+	publish_cycle(P, handed_over);
 }
 
 }  // namespace osc

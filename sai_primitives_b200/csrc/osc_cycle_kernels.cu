@@ -5,6 +5,7 @@
 #include "osc_blend.cuh"
 #include "osc_launch.h"
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #if defined(OSC_TRACE)
 #include <cstdio>
@@ -73,17 +74,34 @@ static bool cycle_spec_eligible(const OscProgram& P, bool has_jt, bool* motion) 
 	return true;
 }
 
+// multiprocessors of the current device (cached per device)
+static int sm_count() {
+	static std::atomic<int> cached[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) dev = 0;
+	int v = cached[dev].load(std::memory_order_relaxed);
+	if (v == 0) {
+		cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+		if (v <= 0) v = 148;
+		cached[dev].store(v, std::memory_order_relaxed);
+	}
+	return v;
+}
+
 template <int N, int R, bool JT, bool FULL, bool SPEC = false, bool GRAV = false, bool MOTION = SPEC>
 static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 	const unsigned grid = (unsigned)((P.n_robots + kCycleBlock - 1) / kCycleBlock);
 	constexpr int smem = cycle_smem_doubles<N, R, SPEC, MOTION>() * kCycleBlock * (int)sizeof(double);
-	static bool configured[64] = {false};  // per device: function attributes belong to the device's context
+	// per device: function attributes belong to the device's context.  Atomic flags: host threads driving different handles
+	// may get here at the same time (setting the attribute twice is harmless, a torn read of a plain bool is not defined).
+	static std::atomic<bool> configured[64];
 	int dev = 0;
 	cudaGetDevice(&dev);
-	if (dev < 0 || dev >= 64 || !configured[dev]) {
+	if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
 		cudaError_t e = cudaFuncSetAttribute(osc_cycle_kernel<N, R, JT, FULL, SPEC, GRAV, MOTION>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e != cudaSuccess) return e;
-		if (dev >= 0 && dev < 64) configured[dev] = true;
+		if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
 	}
 #if defined(OSC_TRACE)
 	static unsigned long long* d_trace = nullptr;
@@ -158,7 +176,8 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 		// latency overlaps the tail of the fast kernel (it waits on griddepcontrol.wait before reading the list).
 		const long long want = (P.n_robots + 63) / 64;
 		cudaLaunchConfig_t cfg{};
-		cfg.gridDim = dim3((unsigned)(want < 148 * OSC_GENERIC_MIN_BLOCKS ? want : 148 * OSC_GENERIC_MIN_BLOCKS));
+		const long long cover = (long long)sm_count() * OSC_GENERIC_MIN_BLOCKS;
+		cfg.gridDim = dim3((unsigned)(P.general_grid_small ? 1 : (want < cover ? want : cover)));
 		cfg.blockDim = dim3(64);
 		cfg.dynamicSmemBytes = 0;
 		cfg.stream = stream;

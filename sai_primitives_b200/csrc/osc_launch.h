@@ -29,6 +29,8 @@ cudaError_t launch_popc_probe(const OscProgram& P, int mft_index, int K, const d
 cudaError_t measure_fp64_peak(double seconds, double* tflops, cudaStream_t stream);
 cudaError_t launch_sim_integrate(const OscProgram& P, double* q, double* dq, const double* tau, double dt, int substeps, cudaStream_t stream);
 cudaError_t launch_jla(const OscProgram& P, cudaStream_t stream);
+// read-only observers (osc_observers.cuh): kind = ObserverKind, task = position in the hierarchy, out = ncomp x N (SoA)
+cudaError_t launch_observer(const OscProgram& P, int task, int kind, double* out, cudaStream_t stream);
 cudaError_t launch_reinit_mft(const OscProgram& P, int mft_index, int full_init, cudaStream_t stream);
 cudaError_t launch_reinit_jt(const OscProgram& P, int jt_index, cudaStream_t stream);
 cudaError_t launch_sensed_wrench(const OscProgram& P, int mft_index, const double* f, const double* m, cudaStream_t stream);

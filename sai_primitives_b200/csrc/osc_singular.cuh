@@ -9,6 +9,7 @@
 // serves the thin band of non-singular robots the sound test rejects, so it implements every branch).
 #pragma once
 #include "osc_kindyn.cuh"
+#include "osc_pipeline.cuh"
 #include "osc_tasks.cuh"
 
 #ifndef OSC_GENERIC_MIN_BLOCKS
@@ -625,6 +626,7 @@ __global__ void __launch_bounds__(64, OSC_GENERIC_MIN_BLOCKS) osc_singular_kerne
 	const int stride = gridDim.x * blockDim.x;
 	for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < count; slot += stride)
 		generic_cycle_one<N>(P, (int64_t)P.sing_list[slot], OSC_STATUS_SINGULAR_PATH);
+	publish_general_done(P, count);
 }
 
 // Whole-batch kernel for hierarchies without a specialised fast kernel (partial joint tasks, several motion-force

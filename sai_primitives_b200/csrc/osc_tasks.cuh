@@ -104,7 +104,15 @@ DEVI void popc_step(const DevMft& t, IDX NR, IDX i, const double fd[3], const do
 	const double power = (dot3(fdiff, vcl) - dot3(Fcmd, vr)) * dt;
 	PO += power;
 	// push
-	if (size == cap) {	// ring full: drop the oldest sample (the reference queue is unbounded)
+	if (size == cap) {
+		// Ring full (the reference queue is unbounded: it only shrinks while the observer total is positive, :49-61).  The oldest
+		// sample leaves the way the reference will eventually pop it: a positive sample is subtracted from the observer.  For
+		// samples <= 0 this is exactly what the reference does later (they are popped without touching the observer), so only a
+		// positive sample that is more than `capacity` cycles old while the observer has stayed <= 0 all along is forgotten early.
+		// From then on the passivity controller's Rc differs from the reference's (tests/test_popc_reference.py measures by how
+		// much); the status bit says that parity is lost.  A ring as long as the longest active episode never gets here.
+		const double front = t.ring[(int64_t)head * NR + i];
+		if (front > 0.0) PO -= front;
 		head = (head + 1) % cap;
 		size--;
 		status |= OSC_STATUS_POPC_OVERFLOW;

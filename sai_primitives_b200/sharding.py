@@ -12,19 +12,19 @@ import numpy as np
 
 
 def shard_range(n_total: int, rank: int, world_size: int):
-    """[lo, hi) of the robots owned by `rank`: sizes differ by at most one, blocks are contiguous and ordered."""
+    """[lo, hi) of the robots owned by `rank`: robot i -> rank floor(i * world_size / n_total), i.e. contiguous,
+    ordered blocks whose sizes differ by at most one.  Same arithmetic as the C entry point osc_shard_range."""
     if not (0 <= rank < world_size):
         raise ValueError("rank out of range")
-    base, rem = divmod(int(n_total), int(world_size))
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    n_total, world_size = int(n_total), int(world_size)
+    lo = -((-rank * n_total) // world_size)
+    hi = -((-(rank + 1) * n_total) // world_size)
+    return lo, hi
 
 
 def shard_of(index: int, n_total: int, world_size: int) -> int:
     """rank that owns robot `index` under shard_range"""
-    base, rem = divmod(int(n_total), int(world_size))
-    cut = rem * (base + 1)
-    return index // (base + 1) if index < cut else rem + (index - cut) // max(base, 1)
+    return (int(index) * int(world_size)) // int(n_total)
 
 
 class ModelGroups:

@@ -2,6 +2,8 @@
 // written against the batched C++ mirror: MotionForceTask at end-effector (0,0,0.07) + JointTask in its null space,
 // RobotController, for N robots.  Usage: host_mirror_demo <state.bin> <N> <tau_out.bin>
 //   state.bin: q (7 x N, SoA) then dq (7 x N, SoA), float64.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -46,9 +48,17 @@ int main(int argc, char** argv) {
 		FILE* o = std::fopen(argv[3], "wb");
 		std::fwrite(tau.data(), 8, tau.size(), o);
 		std::fclose(o);
-		size_t unhandled = 0;
-		for (uint32_t s : robot->status()) unhandled += (s & OSC_STATUS_UNHANDLED) ? 1 : 0;
-		std::printf("ok %lld robots, %zu on the singular path\n", (long long)N, unhandled);
+		size_t unhandled = 0, singular = 0;
+		for (uint32_t s : robot->status()) {
+			unhandled += (s & OSC_STATUS_UNHANDLED) ? 1 : 0;
+			singular += (s & OSC_STATUS_SINGULAR_PATH) ? 1 : 0;
+		}
+		// TemplateTask::getTaskAndPreviousNullspace of the last task of a full hierarchy on a 7-dof arm: the zero matrix
+		std::vector<double> Nall((size_t)49 * N);
+		joint_task->getTaskAndPreviousNullspace(Nall.data());
+		double nmax = 0.0;
+		for (double v : Nall) nmax = std::max(nmax, std::fabs(v));
+		std::printf("ok %lld robots, %zu unhandled, %zu on the singular path, |N_joint N_prec| max %.1e\n", (long long)N, unhandled, singular, nmax);
 	} catch (const std::exception& e) {
 		std::fprintf(stderr, "error: %s\n", e.what());
 		return 1;

@@ -94,3 +94,24 @@ def test_product_does_not_import_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "liboscref" not in txt and "osc_ref.cpp" not in txt, f
+
+
+def test_shard_range_c_and_python_agree(lib):
+    """osc_shard_range (C callers) and sharding.shard_range (Python callers): the same contiguous partition, every robot owned once"""
+    import ctypes as C
+    from sai_primitives_b200.sharding import shard_of, shard_range
+    for n_total in (0, 1, 7, 8, 65536, 65537, 262144, 1000003):
+        for world in (1, 2, 3, 4, 8):
+            covered = 0
+            for r in range(world):
+                first, count = C.c_int64(-1), C.c_int64(-1)
+                assert lib.osc_shard_range(n_total, r, world, C.byref(first), C.byref(count)) == 0
+                lo, hi = shard_range(n_total, r, world)
+                assert (first.value, first.value + count.value) == (lo, hi)
+                assert lo == covered
+                covered = hi
+                if hi > lo:
+                    assert shard_of(lo, n_total, world) == r and shard_of(hi - 1, n_total, world) == r
+            assert covered == n_total
+    first, count = C.c_int64(), C.c_int64()
+    assert lib.osc_shard_range(10, 4, 4, C.byref(first), C.byref(count)) != 0

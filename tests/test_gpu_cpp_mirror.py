@@ -26,7 +26,8 @@ def test_cpp_mirror_example05(tmp_path):
     out = tmp_path / "tau.bin"
     r = subprocess.run([str(exe), str(state), str(N), str(out)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    assert "0 on the singular path" in r.stdout
+    assert "0 unhandled, 0 on the singular path" in r.stdout
+    assert float(r.stdout.strip().split()[-1]) < 1e-9       # a full joint task closes the hierarchy: nothing is left of the null space
     tau = np.fromfile(out, dtype=np.float64).reshape(7, N).T
     link, pt = TASK_POINTS["panda"]
     ob = OracleBatch("panda", N); ob.set_state(q, dq)

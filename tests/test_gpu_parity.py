@@ -621,3 +621,116 @@ def test_full_size_properties_262144_robots():
     cb.mft_set_goals(tm, x0, R0, np.tile([0.02, -0.01, 0.03], (idx.size, 1)), z, z, z); cb.jt_set_goals(tj, q[idx] + 0.05)
     ref = cb.cycle(n_threads=8)
     assert rel_err(tau[idx], ref).max() < REL_TOL
+
+
+def test_pipelined_back_to_back_cycles():
+    """Cross-cycle pipelining (csrc/osc_pipeline.cuh): K cycles enqueued back to back, so that blocks of cycle c + 1 run while
+    the last wave of cycle c is still in flight, with integral gains on both tasks (every cycle reads what the previous one
+    wrote) and unfiltered states (hand-overs to the general path in most blocks, i.e. the dirty-block wait).  The result must be
+    bit-identical to the same cycles run one by one without pipelining, and match the oracle on a sample."""
+    import os
+    import torch
+    import sai_primitives_b200 as sp
+    N, K = 66000, 10
+    base_q, base_dq, _ = sample_states("panda", 1024)
+    rng = np.random.default_rng(5)
+    pick = rng.integers(0, 1024, N)
+    pick[:64] = np.arange(64)
+    q, dq = base_q[pick], base_dq[pick]
+    link, pt = TASK_POINTS["panda"]
+    dev = torch.device("cuda", 0)
+
+    def build(pipelined):
+        if not pipelined:
+            os.environ["SAI_B200_NO_PIPELINE"] = "1"
+        try:
+            robot = sp.BatchedRobot("panda", N)
+        finally:
+            os.environ.pop("SAI_B200_NO_PIPELINE", None)
+        robot.setQ(q); robot.setDq(dq); robot.updateModel()
+        mft = sp.MotionForceTask(robot, link, (np.eye(3), np.array(pt))); jt = sp.JointTask(robot)
+        mft.setPosControlGains(100.0, 20.0, 5.0); mft.setOriControlGains(200.0, 28.3, 4.0); jt.setGains(50.0, 14.0, 3.0)
+        ctrl = sp.RobotController(robot, [mft, jt])
+        mft.setGoalLinearVelocity(np.array([0.02, -0.01, 0.03])); jt.setGoalPosition(q + 0.05)
+        return robot, mft, jt, ctrl
+
+    d_q = torch.from_numpy(np.ascontiguousarray(q.T)).to(dev); d_dq = torch.from_numpy(np.ascontiguousarray(dq.T)).to(dev)
+    out = {}
+    for pipelined in (True, False):
+        robot, mft, jt, ctrl = build(pipelined)
+        d_tau = torch.zeros((7, N), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        for k in range(K):
+            ctrl.stepDevice(d_q.data_ptr(), d_dq.data_ptr(), d_tau.data_ptr())
+            if not pipelined:
+                robot.sync()
+        robot.sync()
+        st = robot.status()
+        assert (st & sp.capi.STATUS_UNHANDLED).sum() == 0
+        out[pipelined] = (d_tau.cpu().numpy().T.copy(), mft._get(sp.capi.MFT_INTEGRATED_POSITION_ERROR), jt._get(sp.capi.JT_INTEGRATED_POSITION_ERROR), st)
+        robot.close()
+    assert ((out[True][3] & sp.capi.STATUS_SINGULAR_PATH) != 0).mean() > 0.3      # most blocks handed robots over
+    for a, b in zip(out[True][:3], out[False][:3]):
+        assert np.array_equal(a, b)
+    ob = OracleBatch("panda", 64); ob.set_state(q[:64], dq[:64])
+    omft = ob.add_mft(link, (np.eye(3), np.array(pt))); ojt = ob.add_jt(); ob.finalize()
+    for i in range(64):
+        omft[i].setPosControlGains(100.0, 20.0, 5.0); omft[i].setOriControlGains(200.0, 28.3, 4.0); ojt[i].setGains(50.0, 14.0, 3.0)
+        omft[i].setGoalLinearVelocity((0.02, -0.01, 0.03)); ojt[i].setGoalPosition(q[i] + 0.05)
+    for k in range(K):
+        ref = ob.cycle()
+    assert rel_err(out[True][0][:64], ref).max() < REL_TOL
+
+
+@pytest.mark.parametrize("case", ["panda_full", "panda_xyz_force", "sliding_partial_joint"])
+def test_task_observers_and_nullspaces(case):
+    """TemplateTask::getTaskNullspace / getPreviousTasksNullspace / getTaskAndPreviousNullspace (TemplateTask.h:74-89),
+    MotionForceTask::getPositionError / getOrientationError / sigma*() (MotionForceTask.h:268-269, :613-616) and the per-cycle
+    observers getCurrentLinearVelocity / getCurrentAngularVelocity / getUnitMassForce, against the reference's own getters."""
+    import sai_primitives_b200 as sp
+    N = 40
+    name = "panda_sliding_base" if case == "sliding_partial_joint" else "panda"
+    q, dq, _ = sample_states(name, N)          # unfiltered: singular robots included (their N goes through the blending branch)
+    n = q.shape[1]
+    link, pt = TASK_POINTS[name]
+    comp = (np.eye(3), np.array(pt))
+    robot = sp.BatchedRobot(name, N)
+    robot.setQ(q); robot.setDq(dq); robot.updateModel()
+    ob = OracleBatch(name, N); ob.set_state(q, dq)
+    if case == "panda_full":
+        gt = [sp.MotionForceTask(robot, link, comp), sp.JointTask(robot)]
+        ot = [ob.add_mft(link, comp), ob.add_jt()]
+    elif case == "panda_xyz_force":
+        xyz = [(1, 0, 0), (0, 1, 0), (0, 0, 1)]
+        gt = [sp.MotionForceTask(robot, link, comp, xyz, [], is_force_motion_parametrization_in_compliant_frame=True), sp.JointTask(robot)]
+        ot = [ob.add_mft(link, comp, xyz, [], in_compliant=True), ob.add_jt()]
+        gt[0].parametrizeForceMotionSpaces(1, (0, 0, 1))
+        for t in ot[0]:
+            t.parametrizeForceMotionSpaces(1, (0, 0, 1))
+    else:
+        S = np.zeros((2, 8)); S[0, 0] = 1; S[1, 7] = 1
+        gt = [sp.JointTask(robot, S, task_name="partial_joint_task"), sp.MotionForceTask(robot, link, comp)]
+        ot = [ob.add_jt(S, name="partial_joint_task"), ob.add_mft(link, comp)]
+    ctrl = sp.RobotController(robot, gt); ob.finalize()
+    mi = 1 if case == "sliding_partial_joint" else 0
+    _set_mft_goals(gt[mi], ot[mi], N)
+    ctrl.updateControllerTaskModels()
+    tau = ctrl.computeControlTorques()
+    assert rel_err(tau, ob.cycle()).max() < REL_TOL
+    for g, o in zip(gt, ot):
+        for name_ in ("getTaskNullspace", "getPreviousTasksNullspace", "getTaskAndPreviousNullspace"):
+            a = getattr(g, name_)()
+            b = np.array([np.asarray(getattr(t, name_)()).reshape(n, n) for t in o])
+            assert a.shape == (N, n, n)
+            assert np.abs(a - b).max() < 1e-8 * max(1.0, np.abs(b).max()), (case, name_)
+    g, o = gt[mi], ot[mi]
+    for name_ in ("getPositionError", "getOrientationError", "getCurrentLinearVelocity", "getCurrentAngularVelocity", "getUnitMassForce",
+                  "sigmaForce", "sigmaPosition", "sigmaMoment", "sigmaOrientation"):
+        a = getattr(g, name_)()
+        b = np.array([np.asarray(getattr(t, name_)()) for t in o]).reshape(a.shape)
+        assert np.abs(a - b).max() < 1e-9 * max(1.0, np.abs(b).max()), (case, name_)
+    # observers can be switched off; the fields then refuse to answer instead of returning stale values
+    robot.enableObservers(False)
+    with pytest.raises(Exception):
+        g.getUnitMassForce()
+    robot.enableObservers(True)
