@@ -391,9 +391,9 @@ int osc_create(const osc_model_desc* model, int64_t n_robots, int device, osc_ha
 	if (!(nopipe && nopipe[0] == '1')) {
 		const size_t blocks = ((size_t)n_robots + osc::kCycleBlock - 1) / osc::kCycleBlock;
 		if ((rc = dev_alloc(h, &h->d_block_epoch, blocks, true)) != OSC_OK) return cleanup(rc);
-		if ((rc = dev_alloc(h, &h->d_general_done, (size_t)2, true)) != OSC_OK) return cleanup(rc);
+		if ((rc = dev_alloc(h, &h->d_general_done, (size_t)4, true)) != OSC_OK) return cleanup(rc);
 		if (cudaHostAlloc((void**)&h->h_seen, sizeof(int32_t), cudaHostAllocMapped) != cudaSuccess) return cleanup(fail(h, OSC_ERR_CUDA, "cudaHostAlloc failed"));
-		*h->h_seen = -1;  // nothing observed yet
+		*h->h_seen = 0;	 // matches general_done[2] == 0: the device rewrites the word only when the count changes
 		int32_t* d_seen = nullptr;
 		if (cudaHostGetDevicePointer((void**)&d_seen, h->h_seen, 0) != cudaSuccess) return cleanup(fail(h, OSC_ERR_CUDA, "cudaHostGetDevicePointer failed"));
 		h->prog.block_epoch = h->d_block_epoch;

@@ -132,7 +132,7 @@ struct OscProgram {
 	// Cycle pipelining (osc_cycle.cuh, "cross-cycle dependencies"): consecutive cycles of one handle depend on each other
 	// robot by robot only, so the fused kernel of cycle c + 1 waits for ITS OWN block of cycle c instead of the whole grid.
 	uint32_t* block_epoch;	 // one word per block of the fused kernel: (cycle number << 1) | handed-robots-over bit
-	uint32_t* general_done;	 // [0] cycle number the general-path kernel has completed, [1] its block completion counter
+	uint32_t* general_done;	 // [0] cycle number the general-path kernel has completed, [1] its block completion counter, [2] count last sent to host_seen
 	int32_t* host_seen;		 // mapped host word: hand-over count of the last completed cycle (a scheduling hint for the host)
 	uint32_t epoch;			 // cycle number of this launch (31 bits used)
 	int32_t general_grid_small;	 // host hint: the last cycles handed nothing over, a handful of general-path blocks is enough

@@ -46,7 +46,8 @@ DEVI void publish_cycle(const OscProgram& P, bool handed_over) {
 	if (threadIdx.x == 0) st_release_u32(P.block_epoch + blockIdx.x, ((P.epoch & kEpochMask) << 1) | (dirty ? 1u : 0u));
 }
 // end of a general-path kernel: the last block to finish clears the list counter it consumed and publishes the cycle number.
-// The hint for the host goes out last and unfenced: it crosses PCIe and nothing on the device waits for it.
+// The hint for the host (a mapped host word) is only rewritten when the count changes: the kernel cannot retire before a
+// write that crosses PCIe has been acknowledged, which costs microseconds of single-cycle latency.
 DEVI void publish_general_done(const OscProgram& P, int32_t count) {
 	if (!P.general_done) return;
 	__syncthreads();
@@ -60,7 +61,10 @@ DEVI void publish_general_done(const OscProgram& P, int32_t count) {
 		if (last) {
 			P.sing_count[P.sing_parity] = 0;
 			st_release_u32(P.general_done, P.epoch);
-			if (P.host_seen) *(volatile int32_t*)P.host_seen = count;
+			if (P.host_seen && (uint32_t)count != P.general_done[2]) {
+				P.general_done[2] = (uint32_t)count;
+				*(volatile int32_t*)P.host_seen = count;
+			}
 		}
 	}
 }
