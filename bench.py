@@ -345,6 +345,7 @@ def gpu_arm(args):
         robot.setQ(q); robot.setDq(dq); robot.updateModel()
         mft = sp.MotionForceTask(robot, LINK, (np.eye(3), np.array(POINT)))
         jt = sp.JointTask(robot)
+        mft.disableInternalOtg(); jt.disableInternalOtg()       # BASELINE config 2: internal OTG off (examples/01-...cpp:136)
         ctrl = sp.RobotController(robot, [mft, jt])
         if goals is None:
             goals = make_goals(rng, mft.getCurrentPosition(), mft.getCurrentOrientation(), q)

@@ -178,6 +178,18 @@ typedef enum {
 	OSC_JT_GOAL_VELOCITY = 33,		 /* (k) */
 	OSC_JT_GOAL_ACCELERATION = 34,	 /* (k) */
 	OSC_JT_INTEGRATED_POSITION_ERROR = 35, /* (k) */
+	/* JointTask::getDesiredPosition / Velocity / Acceleration (JointTask.h:162-176): the state the control law tracks -- the
+	 * internal OTG's output when it is enabled, the goal otherwise (JointTask.cpp:308-319).  Read only. */
+	OSC_JT_DESIRED_POSITION = 36,	  /* (k) */
+	OSC_JT_DESIRED_VELOCITY = 37,	  /* (k) */
+	OSC_JT_DESIRED_ACCELERATION = 38, /* (k) */
+	/* MotionForceTask::getDesired* (MotionForceTask.h:249-266; MotionForceTask.cpp:387-407).  Read only. */
+	OSC_MFT_DESIRED_POSITION = 40,			   /* (3) */
+	OSC_MFT_DESIRED_ORIENTATION = 41,		   /* (9) */
+	OSC_MFT_DESIRED_LINEAR_VELOCITY = 42,	   /* (3) */
+	OSC_MFT_DESIRED_ANGULAR_VELOCITY = 43,	   /* (3) */
+	OSC_MFT_DESIRED_LINEAR_ACCELERATION = 44,  /* (3) */
+	OSC_MFT_DESIRED_ANGULAR_ACCELERATION = 45, /* (3) */
 	/* any task: TemplateTask::getTaskNullspace / getPreviousTasksNullspace / getTaskAndPreviousNullspace
 	 * (TemplateTask.h:74,82,89; JointTask.h:222-226, MotionForceTask.h:205-209), n x n row-major per robot, read only.
 	 * Evaluated on request from the handle's current state: what updateControllerTaskModels() yields at that state. */
@@ -264,6 +276,24 @@ int osc_mft_reset_integrators(osc_handle* h, int task_id, int which);
 int osc_joint_default_params(osc_joint_params* p);
 int osc_joint_get_params(const osc_handle* h, int task_id, osc_joint_params* p);
 int osc_joint_set_params(osc_handle* h, int task_id, const osc_joint_params* p);
+
+/* ---- internal online trajectory generation.  The reference interpolates every task's goal with its
+ * vendored Ruckig by default (JointTask.h:38-42, MotionForceTask.h:67-74): acceleration-limited, phase-synchronised.  Tasks are
+ * created here with the generator OFF (BASELINE.json runs with it off, and so do the reference's examples that call
+ * disableInternalOtg()); the host mirrors switch it on in their constructors to keep the reference's default.
+ *   JointTask::enableInternalOtgAccelerationLimited (JointTask.cpp:358-380): k max velocities and k max accelerations (> 0);
+ *   MotionForceTask::enableInternalOtgAccelerationLimited (MotionForceTask.cpp:511-523);
+ *   disableInternalOtg (JointTask.h:310, MotionForceTask.h:425); getInternalOtgEnabled.
+ * The jerk-limited variants (enableInternalOtgJerkLimited) are not built: OSC_ERR_UNSUPPORTED through the mirrors.
+ * While the generator is on, the goal fields hold the user's goals and the OSC_*_DESIRED_* fields its output. ---- */
+int osc_joint_enable_internal_otg(osc_handle* h, int task_id, const double* max_velocity, const double* max_acceleration);
+int osc_mft_enable_internal_otg(osc_handle* h, int task_id, double max_linear_velocity, double max_linear_acceleration,
+								double max_angular_velocity, double max_angular_acceleration);
+int osc_disable_internal_otg(osc_handle* h, int task_id);
+int osc_internal_otg_enabled(const osc_handle* h, int task_id);
+/* per-robot generator flags of a task (int32 x N): 1 goal reached, 2 recalculation pending, 4 the last update failed (Ruckig
+ * error branch, OTG_joints.cpp:141-149: output held, velocity reset), 8 finished with a residual velocity */
+int osc_get_internal_otg_flags(osc_handle* h, int task_id, int32_t* flags_out, int mem_kind);
 
 /* ---- per-robot fields.  broadcast != 0: data holds ncomp values applied to every robot (host memory only) ---- */
 int osc_field_ncomp(const osc_handle* h, int task_id, int field);

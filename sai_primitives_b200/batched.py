@@ -7,7 +7,8 @@ numpy arrays of shape [n_robots, ncomp] (a single vector of ncomp values is broa
 all robots) or, for zero-copy use, raw device pointers in the SoA layout of the C ABI.
 
 Differences from the reference, by design (BASELINE.json north_star):
-  * internal OTG does not exist on this path (reference default is ON): enabling it raises.
+  * internal OTG: acceleration-limited, phase-synchronised (the reference's default, JointTask.h:38-42 /
+    MotionForceTask.h:67-74) runs batched on the device; the jerk-limited variant is not built and raises.
 """
 from __future__ import annotations
 
@@ -253,6 +254,13 @@ class JointTask(_Task):
 
     task_type = capi.OSC_TASK_JOINT
 
+    class DefaultParameters:
+        """JointTask.h:31-45 (the entries this mirror consults at construction)"""
+        use_internal_otg = True
+        internal_otg_jerk_limited = False
+        otg_max_velocity = math.pi / 3.0
+        otg_max_acceleration = 2.0 * math.pi
+
     def __init__(self, robot: BatchedRobot, joint_selection_matrix=None, task_name="joint_task", loop_timestep=0.001):
         super().__init__(robot, task_name, loop_timestep)
         tid = C.c_int(-1)
@@ -266,6 +274,8 @@ class JointTask(_Task):
         _check(robot.handle, rc)
         self.task_id = tid.value
         self._task_dof = self._lib.osc_get_task_dof(robot.handle, self.task_id)
+        if self.DefaultParameters.use_internal_otg:     # JointTask.cpp:66-80
+            self.enableInternalOtgAccelerationLimited(self.DefaultParameters.otg_max_velocity, self.DefaultParameters.otg_max_acceleration)
 
     def getTaskDof(self):
         return self._task_dof
@@ -285,6 +295,12 @@ class JointTask(_Task):
     def setGoalVelocity(self, v): self._set(capi.JT_GOAL_VELOCITY, v)
     def setGoalAcceleration(self, v): self._set(capi.JT_GOAL_ACCELERATION, v)
     def getGoalPosition(self): return self._get(capi.JT_GOAL_POSITION)
+    def getGoalVelocity(self): return self._get(capi.JT_GOAL_VELOCITY)
+    def getGoalAcceleration(self): return self._get(capi.JT_GOAL_ACCELERATION)
+    # JointTask.h:162-176: what the control law tracks (the internal OTG's output when it is on, the goal otherwise)
+    def getDesiredPosition(self): return self._get(capi.JT_DESIRED_POSITION)
+    def getDesiredVelocity(self): return self._get(capi.JT_DESIRED_VELOCITY)
+    def getDesiredAcceleration(self): return self._get(capi.JT_DESIRED_ACCELERATION)
 
     def setGains(self, kp, kv, ki=0.0):
         kp, kv, ki = (np.atleast_1d(np.asarray(x, dtype=np.float64)) for x in (kp, kv, ki))
@@ -320,22 +336,46 @@ class JointTask(_Task):
     def disableVelocitySaturation(self):
         p = self._params(); p.use_velocity_saturation = 0; self._apply(p)
 
-    def enableInternalOtgAccelerationLimited(self, *a, **k):
-        raise NotImplementedError("internal OTG is excluded from the batched path (BASELINE.json north_star)")
+    def enableInternalOtgAccelerationLimited(self, max_velocity, max_acceleration):
+        """JointTask.cpp:358-380: scalars or vectors of task dof"""
+        k = self._task_dof
+        v = np.atleast_1d(np.asarray(max_velocity, dtype=np.float64)); a = np.atleast_1d(np.asarray(max_acceleration, dtype=np.float64))
+        if v.size == 1 and a.size == 1:
+            v, a = np.full(k, v[0]), np.full(k, a[0])
+        if v.size != k or a.size != k:
+            raise ValueError("max velocity or max acceleration vector size not consistent with task dof in JointTask::enableInternalOtgAccelerationLimited")
+        v, a = np.ascontiguousarray(v), np.ascontiguousarray(a)
+        _check(self._robot.handle, self._lib.osc_joint_enable_internal_otg(self._robot.handle, self.task_id,
+               v.ctypes.data_as(C.POINTER(C.c_double)), a.ctypes.data_as(C.POINTER(C.c_double))))
 
-    enableInternalOtgJerkLimited = enableInternalOtgAccelerationLimited
+    def enableInternalOtgJerkLimited(self, *a, **k):
+        raise NotImplementedError("the jerk-limited internal OTG is not built (OSC_ERR_UNSUPPORTED); use enableInternalOtgAccelerationLimited")
 
     def disableInternalOtg(self):
-        pass
+        _check(self._robot.handle, self._lib.osc_disable_internal_otg(self._robot.handle, self.task_id))
 
     def getInternalOtgEnabled(self):
-        return False
+        return self._lib.osc_internal_otg_enabled(self._robot.handle, self.task_id) == 1
+
+    def getInternalOtgFlags(self):
+        out = np.zeros(self._robot.n_robots, dtype=np.int32)
+        _check(self._robot.handle, self._lib.osc_get_internal_otg_flags(self._robot.handle, self.task_id, out.ctypes.data_as(C.c_void_p), capi.OSC_MEM_HOST))
+        return out
 
 
 class MotionForceTask(_Task):
     """reference src/tasks/MotionForceTask.h:96-110 (both constructors)"""
 
     task_type = capi.OSC_TASK_MOTION_FORCE
+
+    class DefaultParameters:
+        """MotionForceTask.h:40-75 (the entries this mirror consults at construction)"""
+        use_internal_otg = True
+        internal_otg_jerk_limited = False
+        otg_max_linear_velocity = 0.3
+        otg_max_linear_acceleration = 2.0
+        otg_max_angular_velocity = math.pi / 3
+        otg_max_angular_acceleration = 2.0 * math.pi
 
     def __init__(self, robot: BatchedRobot, link_name, compliant_frame=None,
                  controlled_directions_translation=None, controlled_directions_rotation=None,
@@ -367,6 +407,9 @@ class MotionForceTask(_Task):
         _check(robot.handle, self._lib.osc_add_motion_force_task(robot.handle, C.byref(d), C.byref(tid)))
         self.task_id = tid.value
         self._link_name = link_name
+        if self.DefaultParameters.use_internal_otg:     # MotionForceTask.cpp:170-191
+            D = self.DefaultParameters
+            self.enableInternalOtgAccelerationLimited(D.otg_max_linear_velocity, D.otg_max_linear_acceleration, D.otg_max_angular_velocity, D.otg_max_angular_acceleration)
 
     def _params(self):
         p = capi.MftParams()
@@ -524,16 +567,32 @@ class MotionForceTask(_Task):
     def resetIntegratorsAngular(self):
         _check(self._robot.handle, self._lib.osc_mft_reset_integrators(self._robot.handle, self.task_id, 2))
 
-    def enableInternalOtgAccelerationLimited(self, *a, **k):
-        raise NotImplementedError("internal OTG is excluded from the batched path (BASELINE.json north_star)")
+    def enableInternalOtgAccelerationLimited(self, max_linear_velelocity, max_linear_acceleration, max_angular_velocity, max_angular_acceleration):
+        """MotionForceTask.cpp:511-523"""
+        _check(self._robot.handle, self._lib.osc_mft_enable_internal_otg(self._robot.handle, self.task_id, float(max_linear_velelocity),
+               float(max_linear_acceleration), float(max_angular_velocity), float(max_angular_acceleration)))
 
-    enableInternalOtgJerkLimited = enableInternalOtgAccelerationLimited
+    def enableInternalOtgJerkLimited(self, *a, **k):
+        raise NotImplementedError("the jerk-limited internal OTG is not built (OSC_ERR_UNSUPPORTED); use enableInternalOtgAccelerationLimited")
 
     def disableInternalOtg(self):
-        pass
+        _check(self._robot.handle, self._lib.osc_disable_internal_otg(self._robot.handle, self.task_id))
 
     def getInternalOtgEnabled(self):
-        return False
+        return self._lib.osc_internal_otg_enabled(self._robot.handle, self.task_id) == 1
+
+    def getInternalOtgFlags(self):
+        out = np.zeros(self._robot.n_robots, dtype=np.int32)
+        _check(self._robot.handle, self._lib.osc_get_internal_otg_flags(self._robot.handle, self.task_id, out.ctypes.data_as(C.c_void_p), capi.OSC_MEM_HOST))
+        return out
+
+    # MotionForceTask.h:249-266
+    def getDesiredPosition(self): return self._get(capi.MFT_DESIRED_POSITION)
+    def getDesiredOrientation(self): return self._get(capi.MFT_DESIRED_ORIENTATION).reshape(-1, 3, 3)
+    def getDesiredLinearVelocity(self): return self._get(capi.MFT_DESIRED_LINEAR_VELOCITY)
+    def getDesiredAngularVelocity(self): return self._get(capi.MFT_DESIRED_ANGULAR_VELOCITY)
+    def getDesiredLinearAcceleration(self): return self._get(capi.MFT_DESIRED_LINEAR_ACCELERATION)
+    def getDesiredAngularAcceleration(self): return self._get(capi.MFT_DESIRED_ANGULAR_ACCELERATION)
 
 
 class RobotController:

@@ -76,6 +76,19 @@ JT_GOAL_POSITION = 32
 JT_GOAL_VELOCITY = 33
 JT_GOAL_ACCELERATION = 34
 JT_INTEGRATED_POSITION_ERROR = 35
+JT_DESIRED_POSITION = 36
+JT_DESIRED_VELOCITY = 37
+JT_DESIRED_ACCELERATION = 38
+MFT_DESIRED_POSITION = 40
+MFT_DESIRED_ORIENTATION = 41
+MFT_DESIRED_LINEAR_VELOCITY = 42
+MFT_DESIRED_ANGULAR_VELOCITY = 43
+MFT_DESIRED_LINEAR_ACCELERATION = 44
+MFT_DESIRED_ANGULAR_ACCELERATION = 45
+OTG_GOAL_REACHED = 1
+OTG_DIRTY = 2
+OTG_ERROR = 4
+OTG_BAD_FINISH = 8
 TASK_NULLSPACE = 48
 TASK_PREVIOUS_NULLSPACE = 49
 TASK_AND_PREVIOUS_NULLSPACE = 50
@@ -185,6 +198,11 @@ SYMBOLS = {
     "osc_get_status": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "osc_launch_count": (C.c_int64, [_H]),
     "osc_enable_observers": (C.c_int, [_H, C.c_int]),
+    "osc_joint_enable_internal_otg": (C.c_int, [_H, C.c_int, C.POINTER(D), C.POINTER(D)]),
+    "osc_mft_enable_internal_otg": (C.c_int, [_H, C.c_int, D, D, D, D]),
+    "osc_disable_internal_otg": (C.c_int, [_H, C.c_int]),
+    "osc_internal_otg_enabled": (C.c_int, [_H, C.c_int]),
+    "osc_get_internal_otg_flags": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int]),
     "osc_shard_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "osc_urdf_register": (C.c_int, [C.c_char_p, C.c_char_p]),
     "osc_urdf_register_file": (C.c_int, [C.c_char_p, C.c_char_p]),

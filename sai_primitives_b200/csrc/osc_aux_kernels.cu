@@ -1,5 +1,6 @@
 #include "osc_aux_kernels.cuh"
 #include "osc_observers.cuh"
+#include "osc_otg_kernels.cuh"
 #include "osc_launch.h"
 
 namespace osc {
@@ -73,6 +74,18 @@ cudaError_t launch_jla(const OscProgram& P, cudaStream_t stream) {
 	jp.max_torque_ratio_pos_limit = 1.0;
 	jp.max_torque_ratio_vel_limit = 0.05;
 	DISPATCH_N(P.model.n, (jla_kernel<N_><<<grid_for(P.n_robots, 128), 128, 0, stream>>>(P, jp)));
+	return cudaGetLastError();
+}
+cudaError_t launch_otg_update(const OscProgram& P, cudaStream_t stream) {
+	otg_update_kernel<<<grid_for(P.n_robots, 64), 64, 0, stream>>>(P);
+	return cudaGetLastError();
+}
+cudaError_t launch_otg_init(const OscProgram& P, int task, int mode, int fresh, cudaStream_t stream) {
+	DISPATCH_N(P.model.n, (otg_init_kernel<N_><<<grid_for(P.n_robots, 64), 64, 0, stream>>>(P, task, mode, fresh)));
+	return cudaGetLastError();
+}
+cudaError_t launch_otg_disable(const OscProgram& P, int task, cudaStream_t stream) {
+	otg_disable_kernel<<<grid_for(P.n_robots, 64), 64, 0, stream>>>(P, task);
 	return cudaGetLastError();
 }
 cudaError_t launch_observer(const OscProgram& P, int task, int kind, double* out, cudaStream_t stream) {

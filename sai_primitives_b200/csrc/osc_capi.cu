@@ -48,6 +48,7 @@ struct osc_handle {
 	int32_t *d_sing_list = nullptr, *d_sing_count = nullptr;
 	// cycle pipelining (osc_pipeline.cuh): per-block cycle numbers, general-path completion word, mapped host word
 	uint32_t *d_block_epoch = nullptr, *d_general_done = nullptr;
+	int otg_tasks = 0;			  // tasks whose internal OTG is on
 	double* d_sim = nullptr;	  // staging of osc_sim_integrate with host buffers (q, dq, tau)
 	double* d_scratch = nullptr;  // output of the on-request observers (osc_observers.cuh)
 	size_t scratch_doubles = 0;
@@ -259,6 +260,7 @@ struct FieldInfo {
 	int comp;
 	int ncomp;
 	bool writable;
+	bool goal = false;		  // a goal field: lives in the generator's block while the task's internal OTG is on
 	int observer = -1;		  // >= 0: osc::ObserverKind evaluated on request (osc_observers.cuh), comp unused
 	bool needs_observers = false;  // refreshed by the cycle kernels only while osc_enable_observers is on
 };
@@ -268,34 +270,40 @@ bool field_info(const osc_handle* h, int task_id, int field, FieldInfo& fi) {
 	const TaskInfo& t = h->tasks[task_id];
 	const int n = h->model.n;
 	switch (field) {
-		case OSC_TASK_NULLSPACE: fi = {t.type, 0, n * n, false, 0}; return true;
-		case OSC_TASK_PREVIOUS_NULLSPACE: fi = {t.type, 0, n * n, false, 1}; return true;
-		case OSC_TASK_AND_PREVIOUS_NULLSPACE: fi = {t.type, 0, n * n, false, 2}; return true;
+		case OSC_TASK_NULLSPACE: fi = {t.type, 0, n * n, false, false, 0}; return true;
+		case OSC_TASK_PREVIOUS_NULLSPACE: fi = {t.type, 0, n * n, false, false, 1}; return true;
+		case OSC_TASK_AND_PREVIOUS_NULLSPACE: fi = {t.type, 0, n * n, false, false, 2}; return true;
 		default: break;
 	}
 	if (t.type == OSC_TASK_MOTION_FORCE) {
 		switch (field) {
-			case OSC_MFT_POSITION_ERROR: fi = {t.type, 0, 3, false, 3}; return true;
-			case OSC_MFT_ORIENTATION_ERROR: fi = {t.type, 0, 3, false, 4, true}; return true;
-			case OSC_MFT_SIGMA_FORCE: fi = {t.type, 0, 9, false, 5}; return true;
-			case OSC_MFT_SIGMA_POSITION: fi = {t.type, 0, 9, false, 6}; return true;
-			case OSC_MFT_SIGMA_MOMENT: fi = {t.type, 0, 9, false, 7}; return true;
-			case OSC_MFT_SIGMA_ORIENTATION: fi = {t.type, 0, 9, false, 8}; return true;
-			case OSC_MFT_GOAL_POSITION: fi = {t.type, MC_GOAL_POS, 3, true}; return true;
-			case OSC_MFT_GOAL_ORIENTATION: fi = {t.type, MC_GOAL_ORI, 9, true}; return true;
-			case OSC_MFT_GOAL_LINEAR_VELOCITY: fi = {t.type, MC_GOAL_LINVEL, 3, true}; return true;
-			case OSC_MFT_GOAL_ANGULAR_VELOCITY: fi = {t.type, MC_GOAL_ANGVEL, 3, true}; return true;
-			case OSC_MFT_GOAL_LINEAR_ACCELERATION: fi = {t.type, MC_GOAL_LINACC, 3, true}; return true;
-			case OSC_MFT_GOAL_ANGULAR_ACCELERATION: fi = {t.type, MC_GOAL_ANGACC, 3, true}; return true;
+			case OSC_MFT_DESIRED_POSITION: fi = {t.type, MC_GOAL_POS, 3, false}; return true;
+			case OSC_MFT_DESIRED_ORIENTATION: fi = {t.type, MC_GOAL_ORI, 9, false}; return true;
+			case OSC_MFT_DESIRED_LINEAR_VELOCITY: fi = {t.type, MC_GOAL_LINVEL, 3, false}; return true;
+			case OSC_MFT_DESIRED_ANGULAR_VELOCITY: fi = {t.type, MC_GOAL_ANGVEL, 3, false}; return true;
+			case OSC_MFT_DESIRED_LINEAR_ACCELERATION: fi = {t.type, MC_GOAL_LINACC, 3, false}; return true;
+			case OSC_MFT_DESIRED_ANGULAR_ACCELERATION: fi = {t.type, MC_GOAL_ANGACC, 3, false}; return true;
+			case OSC_MFT_POSITION_ERROR: fi = {t.type, 0, 3, false, false, 3}; return true;
+			case OSC_MFT_ORIENTATION_ERROR: fi = {t.type, 0, 3, false, false, 4, true}; return true;
+			case OSC_MFT_SIGMA_FORCE: fi = {t.type, 0, 9, false, false, 5}; return true;
+			case OSC_MFT_SIGMA_POSITION: fi = {t.type, 0, 9, false, false, 6}; return true;
+			case OSC_MFT_SIGMA_MOMENT: fi = {t.type, 0, 9, false, false, 7}; return true;
+			case OSC_MFT_SIGMA_ORIENTATION: fi = {t.type, 0, 9, false, false, 8}; return true;
+			case OSC_MFT_GOAL_POSITION: fi = {t.type, MC_GOAL_POS, 3, true, true}; return true;
+			case OSC_MFT_GOAL_ORIENTATION: fi = {t.type, MC_GOAL_ORI, 9, true, true}; return true;
+			case OSC_MFT_GOAL_LINEAR_VELOCITY: fi = {t.type, MC_GOAL_LINVEL, 3, true, true}; return true;
+			case OSC_MFT_GOAL_ANGULAR_VELOCITY: fi = {t.type, MC_GOAL_ANGVEL, 3, true, true}; return true;
+			case OSC_MFT_GOAL_LINEAR_ACCELERATION: fi = {t.type, MC_GOAL_LINACC, 3, true, true}; return true;
+			case OSC_MFT_GOAL_ANGULAR_ACCELERATION: fi = {t.type, MC_GOAL_ANGACC, 3, true, true}; return true;
 			case OSC_MFT_GOAL_FORCE: fi = {t.type, MC_GOAL_FORCE, 3, true}; return true;
 			case OSC_MFT_GOAL_MOMENT: fi = {t.type, MC_GOAL_MOMENT, 3, true}; return true;
 			case OSC_MFT_CURRENT_POSITION: fi = {t.type, MC_CUR_POS, 3, false}; return true;
 			case OSC_MFT_CURRENT_ORIENTATION: fi = {t.type, MC_CUR_ORI, 9, false}; return true;
-			case OSC_MFT_CURRENT_LINEAR_VELOCITY: fi = {t.type, MC_CUR_LINVEL, 3, false, -1, true}; return true;
-			case OSC_MFT_CURRENT_ANGULAR_VELOCITY: fi = {t.type, MC_CUR_ANGVEL, 3, false, -1, true}; return true;
+			case OSC_MFT_CURRENT_LINEAR_VELOCITY: fi = {t.type, MC_CUR_LINVEL, 3, false, false, -1, true}; return true;
+			case OSC_MFT_CURRENT_ANGULAR_VELOCITY: fi = {t.type, MC_CUR_ANGVEL, 3, false, false, -1, true}; return true;
 			case OSC_MFT_SENSED_FORCE_CONTROL_WORLD: fi = {t.type, MC_SENSED_F, 3, false}; return true;
 			case OSC_MFT_SENSED_MOMENT_CONTROL_WORLD: fi = {t.type, MC_SENSED_M, 3, false}; return true;
-			case OSC_MFT_UNIT_MASS_FORCE: fi = {t.type, MC_UNIT_MASS_FORCE, 6, false, -1, true}; return true;
+			case OSC_MFT_UNIT_MASS_FORCE: fi = {t.type, MC_UNIT_MASS_FORCE, 6, false, false, -1, true}; return true;
 			case OSC_MFT_INTEGRATED_POSITION_ERROR: fi = {t.type, MC_INT_POS, 3, false}; return true;
 			case OSC_MFT_INTEGRATED_ORIENTATION_ERROR: fi = {t.type, MC_INT_ORI, 3, false}; return true;
 			case OSC_MFT_INTEGRATED_FORCE_ERROR: fi = {t.type, MC_INT_FORCE, 3, false}; return true;
@@ -307,10 +315,13 @@ bool field_info(const osc_handle* h, int task_id, int field, FieldInfo& fi) {
 	}
 	const int k = h->prog.jt[t.index].k;
 	switch (field) {
-		case OSC_JT_GOAL_POSITION: fi = {t.type, JC_GOAL_POS, k, true}; return true;
-		case OSC_JT_GOAL_VELOCITY: fi = {t.type, JC_GOAL_VEL, k, true}; return true;
-		case OSC_JT_GOAL_ACCELERATION: fi = {t.type, JC_GOAL_ACC, k, true}; return true;
+		case OSC_JT_GOAL_POSITION: fi = {t.type, JC_GOAL_POS, k, true, true}; return true;
+		case OSC_JT_GOAL_VELOCITY: fi = {t.type, JC_GOAL_VEL, k, true, true}; return true;
+		case OSC_JT_GOAL_ACCELERATION: fi = {t.type, JC_GOAL_ACC, k, true, true}; return true;
 		case OSC_JT_INTEGRATED_POSITION_ERROR: fi = {t.type, JC_INT, k, false}; return true;
+		case OSC_JT_DESIRED_POSITION: fi = {t.type, JC_GOAL_POS, k, false}; return true;
+		case OSC_JT_DESIRED_VELOCITY: fi = {t.type, JC_GOAL_VEL, k, false}; return true;
+		case OSC_JT_DESIRED_ACCELERATION: fi = {t.type, JC_GOAL_ACC, k, false}; return true;
 		default: return false;
 	}
 }
@@ -318,6 +329,20 @@ bool field_info(const osc_handle* h, int task_id, int field, FieldInfo& fi) {
 double* task_state(osc_handle* h, int task_id) {
 	const TaskInfo& t = h->tasks[task_id];
 	return t.type == OSC_TASK_MOTION_FORCE ? h->prog.mft[t.index].st : h->prog.jt[t.index].st;
+}
+
+DevOtg& task_otg(osc_handle* h, int task_id) {
+	const TaskInfo& t = h->tasks[task_id];
+	return t.type == OSC_TASK_MOTION_FORCE ? h->prog.mft[t.index].otg : h->prog.jt[t.index].otg;
+}
+// where a field lives: goal fields move into the generator's block while the task's internal OTG is on
+double* field_storage(osc_handle* h, int task_id, const FieldInfo& fi) {
+	DevOtg& g = task_otg(h, task_id);
+	if (fi.goal && g.enabled) {
+		const int comp = (fi.type == OSC_TASK_MOTION_FORCE) ? OC_USER + fi.comp : OJ_USER_POS + fi.comp;  // JC_GOAL_POS/VEL/ACC = 0/8/16
+		return g.st + (size_t)comp * h->NR;
+	}
+	return task_state(h, task_id) + (size_t)fi.comp * h->NR;
 }
 
 int zero_comps(osc_handle* h, double* st, int comp, int ncomp) {
@@ -756,7 +781,13 @@ static int parametrize_common(osc_handle* h, int task_id, int dim, const double 
 		for (int k = 0; k < 3; k++) cur_axis[k] = a[k];
 	}
 	cur_dim = dim;
-	if (reset) {
+	if (reset && t.otg.enabled) {
+		// the same resets with the internal OTG on: goals and generator together (_otg->reInitializeLinear / Angular, :854, :886)
+		CUDA_TRY(h, osc::launch_otg_init(h->prog, task_id, moment ? 2 : 1, 0, h->stream));
+		h->launches++;
+		if ((rc = zero_comps(h, t.st, moment ? MC_INT_ORI : MC_INT_POS, 3)) != OSC_OK) return rc;
+		if ((rc = zero_comps(h, t.st, moment ? MC_INT_MOMENT : MC_INT_FORCE, 3)) != OSC_OK) return rc;
+	} else if (reset) {
 		if (!moment) {	// MotionForceTask.cpp:850-856
 			CUDA_TRY(h, osc::launch_copy(t.st, h->NR, MC_GOAL_POS, MC_CUR_POS, 3, h->stream));
 			h->launches++;
@@ -944,17 +975,16 @@ int osc_set_field(osc_handle* h, int task_id, int field, const double* data, int
 	if (!field_info(h, task_id, field, fi)) return fail(h, OSC_ERR_INVALID_ARGUMENT, "unknown field for this task");
 	if (!fi.writable) return fail(h, OSC_ERR_INVALID_ARGUMENT, "field is read-only");
 	if (!data) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null data");
-	double* st = task_state(h, task_id);
+	double* dst = field_storage(h, task_id, fi);
 	if (broadcast) {
 		if (mem_kind != OSC_MEM_HOST) return fail(h, OSC_ERR_INVALID_ARGUMENT, "broadcast values must be in host memory");
 		for (int c = 0; c < fi.ncomp; c++)
 			if (!is_finite(data[c])) return fail(h, OSC_ERR_INVALID_ARGUMENT, "non-finite value");
-		CUDA_TRY(h, osc::launch_fill(st, h->NR, fi.comp, fi.ncomp, data, h->stream));
+		CUDA_TRY(h, osc::launch_fill(dst, h->NR, 0, fi.ncomp, data, h->stream));
 		h->launches++;
 		return OSC_OK;
 	}
 	const size_t bytes = (size_t)fi.ncomp * h->NR * sizeof(double);
-	double* dst = st + (size_t)fi.comp * h->NR;
 	if (mem_kind == OSC_MEM_HOST) {
 		CUDA_TRY(h, cudaMemcpyAsync(dst, data, bytes, cudaMemcpyHostToDevice, h->stream));
 		CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -973,7 +1003,7 @@ int osc_get_field(osc_handle* h, int task_id, int field, double* out, int mem_ki
 	if (!out) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null output");
 	if (fi.needs_observers && !h->prog.write_observers)
 		return fail(h, OSC_ERR_STATE, "this field is refreshed by the cycle kernels only while osc_enable_observers(h, 1) is in effect");
-	const double* src = task_state(h, task_id) + (size_t)fi.comp * h->NR;
+	const double* src = field_storage(h, task_id, fi);
 	const size_t bytes = (size_t)fi.ncomp * h->NR * sizeof(double);
 	if (fi.observer >= 0) {
 		if (!h->finalized) return fail(h, OSC_ERR_STATE, "controller not finalized");
@@ -1010,7 +1040,81 @@ int osc_reinitialize_task(osc_handle* h, int task_id) {
 		else
 			CUDA_TRY(h, osc::launch_reinit_jt(h->prog, t.index, h->stream));
 		h->launches++;
+		if (task_otg(h, id).enabled) {	// _otg->reInitialize(current) (JointTask.cpp:106, MotionForceTask.cpp:244)
+			CUDA_TRY(h, osc::launch_otg_init(h->prog, id, 0, 0, h->stream));
+			h->launches++;
+		}
 	}
+	return OSC_OK;
+}
+
+// ---- internal OTG (osc_otg_kernels.cuh)
+static int otg_enable_common(osc_handle* h, int task_id, int dim, const double* vmax, const double* amax) {
+	DevOtg& g = task_otg(h, task_id);
+	for (int a = 0; a < dim; a++) {
+		if (!(vmax[a] > 0.0) || !is_finite(vmax[a])) return fail(h, OSC_ERR_INVALID_ARGUMENT, "max velocity cannot be 0 or negative in any directions in OTG_joints::setMaxVelocity");
+		if (!(amax[a] > 0.0) || !is_finite(amax[a])) return fail(h, OSC_ERR_INVALID_ARGUMENT, "max acceleration cannot be 0 or negative in any directions in OTG_joints::setMaxAcceleration");
+	}
+	const bool is_mft = h->tasks[task_id].type == OSC_TASK_MOTION_FORCE;
+	if (!g.st) {
+		int rc = dev_alloc(h, &g.st, (size_t)(is_mft ? OC_COUNT : OJ_COUNT) * h->NR, true);
+		if (rc != OSC_OK) return rc;
+		if ((rc = dev_alloc(h, &g.flags, (size_t)h->NR, true)) != OSC_OK) return rc;
+	}
+	for (int a = 0; a < OSC_MAX_DOF; a++) {
+		g.vmax[a] = a < dim ? vmax[a] : 1.0;
+		g.amax[a] = a < dim ? amax[a] : 1.0;
+	}
+	const bool was_on = g.enabled != 0;
+	g.enabled = 1;
+	// off -> on: the generator restarts at the current position (JointTask.cpp:372-374, MotionForceTask.cpp:514-516) and the
+	// user's goals stay; already on: new limits only (OTG_joints.cpp:44-92)
+	CUDA_TRY(h, osc::launch_otg_init(h->prog, task_id, was_on ? 3 : 0, was_on ? 0 : 1, h->stream));
+	h->launches++;
+	if (!was_on) h->otg_tasks++;
+	return OSC_OK;
+}
+int osc_joint_enable_internal_otg(osc_handle* h, int task_id, const double* max_velocity, const double* max_acceleration) {
+	ENTER(h);
+	int rc = check_task(h, task_id, OSC_TASK_JOINT);
+	if (rc != OSC_OK) return rc;
+	if (!max_velocity || !max_acceleration) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null limits");
+	return otg_enable_common(h, task_id, h->prog.jt[h->tasks[task_id].index].k, max_velocity, max_acceleration);
+}
+int osc_mft_enable_internal_otg(osc_handle* h, int task_id, double max_linear_velocity, double max_linear_acceleration, double max_angular_velocity,
+								double max_angular_acceleration) {
+	ENTER(h);
+	int rc = check_task(h, task_id, OSC_TASK_MOTION_FORCE);
+	if (rc != OSC_OK) return rc;
+	const double v[6] = {max_linear_velocity, max_linear_velocity, max_linear_velocity, max_angular_velocity, max_angular_velocity, max_angular_velocity};
+	const double a[6] = {max_linear_acceleration, max_linear_acceleration, max_linear_acceleration, max_angular_acceleration, max_angular_acceleration,
+						 max_angular_acceleration};
+	return otg_enable_common(h, task_id, 6, v, a);
+}
+int osc_disable_internal_otg(osc_handle* h, int task_id) {
+	ENTER(h);
+	if (task_id < 0 || task_id >= (int)h->tasks.size()) return fail(h, OSC_ERR_INVALID_ARGUMENT, "task id out of range");
+	DevOtg& g = task_otg(h, task_id);
+	if (!g.enabled) return OSC_OK;
+	CUDA_TRY(h, osc::launch_otg_disable(h->prog, task_id, h->stream));
+	h->launches++;
+	g.enabled = 0;
+	h->otg_tasks--;
+	return OSC_OK;
+}
+int osc_internal_otg_enabled(const osc_handle* h, int task_id) {
+	if (!h || task_id < 0 || task_id >= (int)h->tasks.size()) return OSC_ERR_INVALID_ARGUMENT;
+	return task_otg(const_cast<osc_handle*>(h), task_id).enabled ? 1 : 0;
+}
+int osc_get_internal_otg_flags(osc_handle* h, int task_id, int32_t* flags_out, int mem_kind) {
+	ENTER(h);
+	if (task_id < 0 || task_id >= (int)h->tasks.size()) return fail(h, OSC_ERR_INVALID_ARGUMENT, "task id out of range");
+	if (!flags_out) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null output");
+	DevOtg& g = task_otg(h, task_id);
+	if (!g.enabled) return fail(h, OSC_ERR_STATE, "internal OTG is not enabled on this task");
+	const size_t bytes = (size_t)h->NR * sizeof(int32_t);
+	CUDA_TRY(h, cudaMemcpyAsync(flags_out, g.flags, bytes, mem_kind == OSC_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+	if (mem_kind == OSC_MEM_HOST) CUDA_TRY(h, cudaStreamSynchronize(h->stream));
 	return OSC_OK;
 }
 
@@ -1068,6 +1172,10 @@ static int run_cycle(osc_handle* h, double* tau_out, int mem_kind, bool sync_hos
 		h->prog.general_grid_small = h->clean_cycles >= 4 ? 1 : 0;
 	}
 	cudaError_t e;
+	if (h->otg_tasks > 0) {	 // the tasks' internal OTG produces this cycle's desired state first (JointTask.cpp:313-319, MotionForceTask.cpp:394-407)
+		CUDA_TRY(h, osc::launch_otg_update(h->prog, h->stream));
+		h->launches += 1;
+	}
 	if (h->jla_enabled) {
 		// RobotController.cpp:96-116: the avoidance blend comes after the task torques (and their saturation) and before
 		// gravity compensation, so the cycle kernels leave gravity to the avoidance kernel

@@ -69,6 +69,19 @@ struct DevModel {
 	double gravity[3];	// world frame
 };
 
+// Internal OTG of one task (osc_otg.h / osc_otg_kernels.cuh).  While enabled, the task's goal slots (JC_GOAL_* / MC_GOAL_*)
+// hold the DESIRED state the generator produced for this cycle -- the control laws read nothing else -- and the goals the user
+// sets live in the generator's own block.
+enum OtgJointComp : int { OJ_USER_POS = 0, OJ_USER_VEL = 8, OJ_USER_ACC = 16, OJ_CORE = 24, OJ_CORE_DOUBLES = 226, OJ_COUNT = 250 };
+enum OtgCartComp : int { OC_USER = 0 /* 24, same order as MC_GOAL_POS .. MC_GOAL_ANGACC */, OC_CORE = 24, OC_CORE_DOUBLES = 191, OC_COUNT = 215 };
+struct DevOtg {
+	int32_t enabled;
+	int32_t pad;
+	double vmax[OSC_MAX_DOF], amax[OSC_MAX_DOF];  // motion-force task: linear x 3, angular x 3
+	double* st;		 // OJ_COUNT / OC_COUNT x N
+	int32_t* flags;	 // N (otg::OtgFlags)
+};
+
 struct DevMft {
 	int32_t body;
 	int32_t rank, pos_range, ori_range;
@@ -84,6 +97,7 @@ struct DevMft {
 	double* st;	   // MC_COUNT x N
 	int32_t* ist;  // MI_COUNT x N
 	double* ring;  // ring_capacity x N (or null)
+	DevOtg otg;
 };
 
 struct DevJt {
@@ -93,6 +107,7 @@ struct DevJt {
 	double dt;
 	osc_joint_params p;
 	double* st;	 // JC_COUNT x N
+	DevOtg otg;
 };
 
 // JointLimitAvoidanceTask parameters (JointLimitAvoidanceTask.h:26-35; the reference has no setters for them)

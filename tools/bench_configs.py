@@ -8,6 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import sai_primitives_b200 as sp
+from sai_primitives_b200 import batched as _b
+_b.JointTask.DefaultParameters.use_internal_otg = False      # BASELINE configs: internal OTG off
+_b.MotionForceTask.DefaultParameters.use_internal_otg = False
 import bench
 
 def timed(ctrl, robot, q_t, dq_t, tau_t, steps=100, warm=10):
