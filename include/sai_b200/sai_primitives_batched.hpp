@@ -4,8 +4,9 @@
 //   - broadcast: one value for all robots (same signature shape as the reference, plain arrays instead of Eigen);
 //   - batched:   a pointer to SoA data (component-major, data[c * n_robots + i]) in host or device memory.
 // Errors the reference reports with std::invalid_argument are re-thrown as std::invalid_argument.
-// Internal OTG (reference default ON) is not part of this path: the mirrors start with it off and
-// enableInternalOtg* throws.
+// Internal OTG: the acceleration-limited, phase-synchronised generator (the reference's default, JointTask.h:38-42,
+// MotionForceTask.h:67-74) runs batched on the device and is ON after construction like in the reference; the jerk-limited
+// variant is not built (enableInternalOtgJerkLimited throws).
 #pragma once
 
 #include <array>
@@ -132,10 +133,16 @@ protected:
 // src/tasks/JointTask.h
 class JointTask : public TemplateTask {
 public:
+	struct DefaultParameters {	// JointTask.h:31-45 (the entries this mirror consults)
+		static constexpr bool use_internal_otg = true;
+		static constexpr double otg_max_velocity = 3.14159265358979323846 / 3.0;
+		static constexpr double otg_max_acceleration = 2.0 * 3.14159265358979323846;
+	};
 	JointTask(std::shared_ptr<BatchedRobot>& robot, const std::string& task_name = "joint_task", double loop_timestep = 0.001)
 		: TemplateTask(robot, task_name, JOINT_TASK, loop_timestep) {
 		check(h(), osc_add_joint_task(h(), nullptr, 0, loop_timestep, &_id));
 		_task_dof = osc_get_task_dof(h(), _id);
+		if (DefaultParameters::use_internal_otg) enableInternalOtgAccelerationLimited(DefaultParameters::otg_max_velocity, DefaultParameters::otg_max_acceleration);
 	}
 	// joint_selection_matrix: row-major k x dof
 	JointTask(std::shared_ptr<BatchedRobot>& robot, const std::vector<double>& joint_selection_matrix, int rows,
@@ -145,6 +152,7 @@ public:
 			throw std::invalid_argument("joint selection matrix size not consistent with robot dof in JointTask constructor\n");
 		check(h(), osc_add_joint_task(h(), joint_selection_matrix.data(), rows, loop_timestep, &_id));
 		_task_dof = osc_get_task_dof(h(), _id);
+		if (DefaultParameters::use_internal_otg) enableInternalOtgAccelerationLimited(DefaultParameters::otg_max_velocity, DefaultParameters::otg_max_acceleration);
 	}
 	int getTaskDof() const { return _task_dof; }
 	bool isFullJointTask() const { return _task_dof == _robot->dof(); }
@@ -199,10 +207,22 @@ public:
 		p.use_velocity_saturation = 0;
 		apply(p);
 	}
-	void enableInternalOtgAccelerationLimited(double, double) { throw std::logic_error("internal OTG is excluded from the batched path"); }
-	void enableInternalOtgJerkLimited(double, double, double) { throw std::logic_error("internal OTG is excluded from the batched path"); }
-	void disableInternalOtg() {}
-	bool getInternalOtgEnabled() const { return false; }
+	// JointTask.cpp:358-380
+	void enableInternalOtgAccelerationLimited(double max_velocity, double max_acceleration) {
+		enableInternalOtgAccelerationLimited(std::vector<double>(_task_dof, max_velocity), std::vector<double>(_task_dof, max_acceleration));
+	}
+	void enableInternalOtgAccelerationLimited(const std::vector<double>& max_velocity, const std::vector<double>& max_acceleration) {
+		sized(max_velocity, "max velocity");
+		sized(max_acceleration, "max acceleration");
+		check(h(), osc_joint_enable_internal_otg(h(), _id, max_velocity.data(), max_acceleration.data()));
+	}
+	void enableInternalOtgJerkLimited(double, double, double) { throw std::logic_error("the jerk-limited internal OTG is not built"); }
+	void disableInternalOtg() { check(h(), osc_disable_internal_otg(h(), _id)); }
+	bool getInternalOtgEnabled() const { return osc_internal_otg_enabled(h(), _id) == 1; }
+	// JointTask.h:162-176 (SoA k x N out)
+	void getDesiredPosition(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_JT_DESIRED_POSITION, soa, w); }
+	void getDesiredVelocity(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_JT_DESIRED_VELOCITY, soa, w); }
+	void getDesiredAcceleration(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_JT_DESIRED_ACCELERATION, soa, w); }
 
 private:
 	void sized(const std::vector<double>& v, const char* what) const {
@@ -227,6 +247,7 @@ public:
 		osc_mft_desc d = base_desc(link_name, compliant_frame, is_force_motion_parametrization_in_compliant_frame, loop_timestep);
 		d.partial = 0;
 		check(h(), osc_add_motion_force_task(h(), &d, &_id));
+		defaultOtg();
 	}
 	MotionForceTask(std::shared_ptr<BatchedRobot>& robot, const std::string& link_name, const std::vector<Vec3>& controlled_directions_translation,
 					const std::vector<Vec3>& controlled_directions_rotation, const Affine& compliant_frame = Affine(),
@@ -244,6 +265,7 @@ public:
 		for (int i = 0; i < d.n_dirs_rotation; i++)
 			for (int k = 0; k < 3; k++) d.dirs_rotation[i][k] = controlled_directions_rotation[i][k];
 		check(h(), osc_add_motion_force_task(h(), &d, &_id));
+		defaultOtg();
 	}
 
 	// ---- goals: broadcast (reference signatures) and batched SoA
@@ -366,12 +388,26 @@ public:
 	void resetIntegrators() { check(h(), osc_mft_reset_integrators(h(), _id, 0)); }
 	void resetIntegratorsLinear() { check(h(), osc_mft_reset_integrators(h(), _id, 1)); }
 	void resetIntegratorsAngular() { check(h(), osc_mft_reset_integrators(h(), _id, 2)); }
-	void enableInternalOtgAccelerationLimited(double, double, double, double) { throw std::logic_error("internal OTG is excluded from the batched path"); }
-	void enableInternalOtgJerkLimited(double, double, double, double, double, double) { throw std::logic_error("internal OTG is excluded from the batched path"); }
-	void disableInternalOtg() {}
-	bool getInternalOtgEnabled() const { return false; }
+	// MotionForceTask.cpp:511-523
+	void enableInternalOtgAccelerationLimited(double max_linear_velelocity, double max_linear_acceleration, double max_angular_velocity,
+											  double max_angular_acceleration) {
+		check(h(), osc_mft_enable_internal_otg(h(), _id, max_linear_velelocity, max_linear_acceleration, max_angular_velocity, max_angular_acceleration));
+	}
+	void enableInternalOtgJerkLimited(double, double, double, double, double, double) { throw std::logic_error("the jerk-limited internal OTG is not built"); }
+	void disableInternalOtg() { check(h(), osc_disable_internal_otg(h(), _id)); }
+	bool getInternalOtgEnabled() const { return osc_internal_otg_enabled(h(), _id) == 1; }
+	// MotionForceTask.h:249-266 (SoA out)
+	void getDesiredPosition(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_DESIRED_POSITION, soa, w); }
+	void getDesiredOrientation(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_DESIRED_ORIENTATION, soa, w); }
+	void getDesiredLinearVelocity(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_DESIRED_LINEAR_VELOCITY, soa, w); }
+	void getDesiredAngularVelocity(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_DESIRED_ANGULAR_VELOCITY, soa, w); }
+	void getDesiredLinearAcceleration(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_DESIRED_LINEAR_ACCELERATION, soa, w); }
+	void getDesiredAngularAcceleration(double* soa, osc_mem_kind w = OSC_MEM_HOST) const { get(OSC_MFT_DESIRED_ANGULAR_ACCELERATION, soa, w); }
 
 private:
+	void defaultOtg() {	 // MotionForceTask.h:67-74, MotionForceTask.cpp:170-191
+		enableInternalOtgAccelerationLimited(0.3, 2.0, 3.14159265358979323846 / 3.0, 2.0 * 3.14159265358979323846);
+	}
 	osc_mft_desc base_desc(const std::string& link_name, const Affine& c, bool in_compliant, double dt) {
 		osc_mft_desc d{};
 		d.link = _robot->linkFrame(link_name);

@@ -218,6 +218,15 @@ int osc_builtin_link(const char* robot_name, const char* link_name, osc_link_fra
 int osc_urdf_register(const char* model_name, const char* urdf_xml);
 int osc_urdf_register_file(const char* model_name, const char* path);
 const char* osc_urdf_last_error(void);
+/* SaiModel::URDF_FOLDERS[prefix_name] = folder and SaiModel::ReplaceUrdfPathPrefix (examples/01-joint_control/01-joint_control.cpp:40-71):
+ * "${PREFIX}/file" in any path handed to this library is replaced by the registered folder. */
+int osc_urdf_set_folder(const char* prefix_name, const char* folder);
+int osc_urdf_replace_path_prefix(const char* path, char* out, int out_capacity);
+/* World file (examples/15-haptic_control_impedance_type/world.urdf): <world gravity="..."><robot name="R"><model dir="${...}" path="x.urdf"/>
+ * <origin xyz rpy/></robot>...  Loads the URDF of robot `robot_name_in_world`, registers it under `model_name` and sets the
+ * description's R_world_base / t_world_base to the robot's <origin>: sim->getRobotBaseTransform(name) + robot->setTRobotBase(T)
+ * (examples/15-...cpp:124-126).  gravity_out (may be NULL) receives the world's gravity attribute. */
+int osc_world_register_robot(const char* world_file, const char* robot_name_in_world, const char* model_name, double gravity_out[3]);
 
 /* ---- lifetime.  Replaces make_shared<SaiModel>(urdf) + task/controller construction ---- */
 int osc_create(const osc_model_desc* model, int64_t n_robots, int device, osc_handle** out);

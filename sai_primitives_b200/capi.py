@@ -207,6 +207,9 @@ SYMBOLS = {
     "osc_urdf_register": (C.c_int, [C.c_char_p, C.c_char_p]),
     "osc_urdf_register_file": (C.c_int, [C.c_char_p, C.c_char_p]),
     "osc_urdf_last_error": (C.c_char_p, []),
+    "osc_urdf_set_folder": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "osc_urdf_replace_path_prefix": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
+    "osc_world_register_robot": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(D)]),
     "osc_debug_popc_sequence": (C.c_int, [_H, C.c_int, C.c_int, _PD, _PD, _PD, _PD, C.c_double, C.c_double, _PD]),
     "osc_measure_fp64_peak": (C.c_int, [_H, C.c_double, _PD]),
     "osc_sim_integrate": (C.c_int, [_H, _PD, _PD, _PD, C.c_double, C.c_int, C.c_int]),

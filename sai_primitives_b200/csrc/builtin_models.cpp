@@ -544,6 +544,142 @@ extern "C" int osc_urdf_register_file(const char* model_name, const char* path) 
 
 extern "C" const char* osc_urdf_last_error(void) { return urdf_error().c_str(); }
 
+// ---- ${PREFIX} substitution and world files -------------------------------------------------------
+// The reference's examples name their files "${EXAMPLE_15_FOLDER}/world.urdf", "${SAI_MODEL_URDF_FOLDER}/panda/panda_arm.urdf"
+// and resolve them with SaiModel::URDF_FOLDERS / SaiModel::ReplaceUrdfPathPrefix
+// (examples/01-joint_control/01-joint_control.cpp:40-71); the robot's base pose comes from the <robot><origin> element of the
+// world file (sim->getRobotBaseTransform + robot->setTRobotBase, examples/15-haptic_control_impedance_type/...cpp:124-126).
+namespace {
+std::map<std::string, std::string>& urdf_folders() {
+	static std::map<std::string, std::string> m;
+	return m;
+}
+std::string replace_prefixes(const std::string& in, std::string& why) {
+	std::string out;
+	size_t pos = 0;
+	for (;;) {
+		const size_t a = in.find("${", pos);
+		if (a == std::string::npos) {
+			out += in.substr(pos);
+			return out;
+		}
+		const size_t b = in.find('}', a);
+		if (b == std::string::npos) {
+			why = "unterminated ${ in [" + in + "]";
+			return in;
+		}
+		const std::string key = in.substr(a + 2, b - a - 2);
+		auto it = urdf_folders().find(key);
+		if (it == urdf_folders().end()) {
+			why = "prefix ${" + key + "} is not set (osc_urdf_set_folder)";
+			return in;
+		}
+		out += in.substr(pos, a - pos) + it->second;
+		pos = b + 1;
+	}
+}
+bool read_file(const std::string& path, std::string& xml) {
+	FILE* f = std::fopen(path.c_str(), "rb");
+	if (!f) return false;
+	char buf[65536];
+	size_t n;
+	while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) xml.append(buf, n);
+	std::fclose(f);
+	return true;
+}
+}  // namespace
+
+extern "C" int osc_urdf_set_folder(const char* prefix_name, const char* folder) {
+	if (!prefix_name || !folder || !*prefix_name) return OSC_ERR_INVALID_ARGUMENT;
+	urdf_folders()[prefix_name] = folder;
+	return OSC_OK;
+}
+
+extern "C" int osc_urdf_replace_path_prefix(const char* path, char* out, int out_capacity) {
+	if (!path || !out || out_capacity <= 0) return OSC_ERR_INVALID_ARGUMENT;
+	std::string why;
+	const std::string r = replace_prefixes(path, why);
+	if (!why.empty()) {
+		urdf_error() = why;
+		return OSC_ERR_INVALID_ARGUMENT;
+	}
+	if ((int)r.size() + 1 > out_capacity) {
+		urdf_error() = "output buffer too small";
+		return OSC_ERR_INVALID_ARGUMENT;
+	}
+	std::memcpy(out, r.c_str(), r.size() + 1);
+	return OSC_OK;
+}
+
+extern "C" int osc_world_register_robot(const char* world_file, const char* robot_name_in_world, const char* model_name, double gravity_out[3]) {
+	if (!world_file || !robot_name_in_world || !model_name) {
+		urdf_error() = "null argument";
+		return OSC_ERR_INVALID_ARGUMENT;
+	}
+	std::string why;
+	const std::string wpath = replace_prefixes(world_file, why);
+	std::string xml;
+	if (why.empty() && !read_file(wpath, xml)) why = "cannot open [" + wpath + "]";
+	if (!why.empty()) {
+		urdf_error() = why;
+		return OSC_ERR_INVALID_ARGUMENT;
+	}
+	size_t pos = 0;
+	XmlTag t;
+	bool in_robot = false, found = false;
+	int depth_in_robot = 0;
+	std::string dir, file;
+	V3 xyz{0, 0, 0}, rpy_{0, 0, 0}, gravity{0, 0, -9.81};
+	while (next_tag(xml, pos, t)) {
+		if (!in_robot) {
+			if (t.name == "world" && !t.closing && t.attr.count("gravity")) gravity = parse_v3(t.attr["gravity"], gravity);
+			if (t.name == "robot" && !t.closing && t.attr.count("name") && t.attr["name"] == robot_name_in_world) {
+				in_robot = true;
+				found = true;
+				depth_in_robot = 0;
+			}
+			continue;
+		}
+		if (t.closing) {
+			if (depth_in_robot == 0 && t.name == "robot") break;
+			depth_in_robot--;
+			continue;
+		}
+		if (depth_in_robot == 0 && t.name == "model") {
+			dir = t.attr.count("dir") ? t.attr["dir"] : "";
+			file = t.attr.count("path") ? t.attr["path"] : "";
+		} else if (depth_in_robot == 0 && t.name == "origin") {
+			if (t.attr.count("xyz")) xyz = parse_v3(t.attr["xyz"], xyz);
+			if (t.attr.count("rpy")) rpy_ = parse_v3(t.attr["rpy"], rpy_);
+		}
+		if (!t.self_closing) depth_in_robot++;
+	}
+	if (!found || file.empty()) {
+		urdf_error() = std::string("robot [") + robot_name_in_world + "] with a <model path=...> not found in [" + wpath + "]";
+		return OSC_ERR_INVALID_ARGUMENT;
+	}
+	const std::string upath = replace_prefixes(dir.empty() ? file : dir + "/" + file, why);
+	if (!why.empty()) {
+		urdf_error() = why;
+		return OSC_ERR_INVALID_ARGUMENT;
+	}
+	const int rc = osc_urdf_register_file(model_name, upath.c_str());
+	if (rc != OSC_OK) return rc;
+	// SaiModel::setTRobotBase(T_world_robot): R = Rz(yaw) Ry(pitch) Rx(roll) of the <origin> (URDF convention)
+	Built& b = registered()[model_name];
+	const M3 R = rpy(rpy_.x, rpy_.y, rpy_.z);
+	for (int i = 0; i < 9; i++) b.desc.R_world_base[i] = R.m[i];
+	b.desc.t_world_base[0] = xyz.x;
+	b.desc.t_world_base[1] = xyz.y;
+	b.desc.t_world_base[2] = xyz.z;
+	if (gravity_out) {
+		gravity_out[0] = gravity.x;
+		gravity_out[1] = gravity.y;
+		gravity_out[2] = gravity.z;
+	}
+	return OSC_OK;
+}
+
 extern "C" int osc_builtin_model(const char* robot_name, osc_model_desc* out) {
 	const Built* b = lookup(robot_name);
 	if (!b || !out) return OSC_ERR_INVALID_ARGUMENT;

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 #ifndef OSC_NO_PREFETCH
 	prefetch_block_rows<N, R, HAS_JT>(P, blockIdx.x);
 #endif
-	wait_previous_cycle(P);
+	grid_dependency_wait(P);
 	if (!P.block_epoch && i_raw == 0 && P.sing_count) P.sing_count[P.sing_parity ^ 1] = 0;
 	bool handed_over = false;
 	double q[N];
@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		double pid[N], acc[N];
 #pragma unroll
 		for (int j = 0; j < N; j++) pid[j] = acc[j] = 0.0;
+		wait_previous_cycle(P);	 // first access to task state
 		if (alive) {
 			double dq[N];
 #pragma unroll
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 						for (int b = 0; b <= a; b++) G[a][b] += cr[a] * cr[b];
 				}
 			}
+			wait_previous_cycle(P);	 // first access to task state (nothing above reads anything a control cycle writes)
 			if constexpr (MOTION) mft_stage_goals(t, NR, i, smt + (size_t)(kSmFactor<N> + N * R) * sms, sms);
 #pragma unroll
 			for (int j = 0; j < (SPEC ? 0 : N); j++) {

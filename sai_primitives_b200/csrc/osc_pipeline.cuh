@@ -23,13 +23,13 @@ DEVI uint32_t ld_acquire_u32(const uint32_t* p) {
 DEVI void st_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 constexpr uint32_t kEpochMask = 0x7fffffffu;
 
-// start of the fused kernel: wait until this block's robots have finished the previous cycle
+// Wait until this block's robots have finished the previous cycle.  Called by every warp right before its first access to
+// task state (goals staged through shared memory, integrators, handler memory) -- the kinematics and dynamics in front of that
+// point only read q, which no cycle writes -- so the round trip to the flag hides behind the first third of the kernel, and
+// there is no block-wide barrier (lane 0 of each warp polls, the warp reconverges).
 DEVI void wait_previous_cycle(const OscProgram& P) {
-	if (!P.block_epoch) {
-		asm volatile("griddepcontrol.wait;" ::: "memory");
-		return;
-	}
-	if (threadIdx.x == 0) {
+	if (!P.block_epoch) return;	 // whole-grid dependency: griddepcontrol.wait at the top of the kernel (grid_dependency_wait)
+	if ((threadIdx.x & 31) == 0) {
 		const uint32_t want = (P.epoch - 1u) & kEpochMask;
 		uint32_t f;
 		while (((f = ld_acquire_u32(P.block_epoch + blockIdx.x)) >> 1) != want) __nanosleep(64);
@@ -37,7 +37,10 @@ DEVI void wait_previous_cycle(const OscProgram& P) {
 			while ((int32_t)(ld_acquire_u32(P.general_done) - (P.epoch - 1u)) < 0) __nanosleep(256);
 		}
 	}
-	__syncthreads();
+	__syncwarp();
+}
+DEVI void grid_dependency_wait(const OscProgram& P) {
+	if (!P.block_epoch) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 // end of the fused kernel (every thread of the block gets here): publish the cycle number
 DEVI void publish_cycle(const OscProgram& P, bool handed_over) {

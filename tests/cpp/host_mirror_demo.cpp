@@ -27,6 +27,7 @@ int main(int argc, char** argv) {
 		auto motion_force_task = std::make_shared<MotionForceTask>(robot, "end-effector", Affine::Translation(0.0, 0.0, 0.07));
 		motion_force_task->disableInternalOtg();
 		auto joint_task = std::make_shared<JointTask>(robot);
+		joint_task->disableInternalOtg();  // like the reference's examples (examples/01-joint_control/01-joint_control.cpp:136)
 		std::vector<std::shared_ptr<TemplateTask>> task_list = {motion_force_task, joint_task};
 		auto robot_controller = std::make_unique<RobotController>(robot, task_list);
 

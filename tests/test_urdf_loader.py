@@ -92,3 +92,42 @@ def test_reference_urdf_files_give_the_builtin_models(name, path):
     lib = capi.load_library()
     sp.registerUrdf("ref_" + name, os.path.join(REF, path))
     _same_model(_desc_arrays(lib, capi, "ref_" + name), _desc_arrays(lib, capi, name), tol=1e-12)
+
+
+def test_world_file_and_path_prefixes(tmp_path):
+    """SaiModel::URDF_FOLDERS / ReplaceUrdfPathPrefix and the robot's base pose from the world file
+    (examples/01-joint_control/01-joint_control.cpp:40-71, examples/15-...cpp:124-126)"""
+    import ctypes as C
+    from sai_primitives_b200 import capi
+    lib = capi.load_library()
+    from oracle.robots import rpy_to_matrix, rrrr_description
+    (tmp_path / "models").mkdir()
+    (tmp_path / "models" / "arm.urdf").write_text(_urdf_text(rrrr_description()))
+    (tmp_path / "world.urdf").write_text('''<?xml version="1.0" ?>
+<world name="demo_world" gravity="0.0 0.0 -1.62">
+  <robot name="OTHER"><model dir="${MODELS}" path="missing.urdf" name="x" /><origin xyz="9 9 9" rpy="0 0 0" /></robot>
+  <robot name="ARM">
+    <model dir="${MODELS}" path="arm.urdf" name="rrrr" />
+    <origin xyz="0.1 -0.2 0.3" rpy="0.2 -0.4 1.1" />
+  </robot>
+  <static_object name="Floor"><origin xyz="0 0 0" rpy="0 0 0" /></static_object>
+</world>''')
+    assert lib.osc_urdf_set_folder(b"MODELS", str(tmp_path / "models").encode()) == 0
+    assert lib.osc_urdf_set_folder(b"WORLD_DIR", str(tmp_path).encode()) == 0
+    buf = C.create_string_buffer(512)
+    assert lib.osc_urdf_replace_path_prefix(b"${MODELS}/arm.urdf", buf, 512) == 0
+    assert buf.value.decode() == str(tmp_path / "models" / "arm.urdf")
+    assert lib.osc_urdf_replace_path_prefix(b"${NOT_SET}/arm.urdf", buf, 512) != 0
+    g = (C.c_double * 3)()
+    assert lib.osc_world_register_robot(b"${WORLD_DIR}/world.urdf", b"ARM", b"world_arm", g) == 0, lib.osc_urdf_last_error()
+    assert list(g) == [0.0, 0.0, -1.62]
+    d = capi.ModelDesc()
+    assert lib.osc_builtin_model(b"world_arm", C.byref(d)) == 0
+    assert d.n == 4
+    assert np.abs(np.array(d.R_world_base[:]).reshape(3, 3) - rpy_to_matrix((0.2, -0.4, 1.1))).max() < 1e-15
+    assert list(d.t_world_base[:]) == [0.1, -0.2, 0.3]
+    base = _desc_arrays(lib, capi, "rrrr"); got = _desc_arrays(lib, capi, "world_arm")
+    for k in ("axis", "t_fix", "mass", "com", "inertia"):
+        assert np.abs(np.asarray(base[k]) - np.asarray(got[k])).max() < 1e-12, k
+    assert lib.osc_world_register_robot(b"${WORLD_DIR}/world.urdf", b"NOBODY", b"w2", None) != 0
+    assert lib.osc_world_register_robot(b"${WORLD_DIR}/world.urdf", b"OTHER", b"w3", None) != 0      # its URDF does not exist
