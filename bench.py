@@ -304,6 +304,40 @@ def goals_from_poses(q, rng):
     return make_goals(rng, p + Rr @ p_local, Rr @ R_lb, q)
 
 
+# ------------------------------------------------------------------ host memory placement
+def place_host_memory_near_gpu(local_rank):
+    """Best effort, before any pinned allocation: prefer host memory (and CPUs) of the NUMA node the GPU hangs off, so that the
+    ranks of one box do not all stage their host buffers through one socket.  Returns what was found and done (reported under
+    e2e.host_placement); does nothing when the platform hides the topology (numa_node = -1, single node, restricted cpuset)."""
+    info = {"gpu_numa_node": None, "nodes_online": None, "mempolicy": "unchanged", "cpus": "unchanged"}
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"], text=True).strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # sysfs uses a 4-digit domain
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        info["gpu_numa_node"] = node
+        info["nodes_online"] = open("/sys/devices/system/node/online").read().strip()
+        if node < 0 or info["nodes_online"] in ("0", ""):
+            return info
+        libc = C.CDLL(None, use_errno=True)
+        mask = C.c_ulong(1 << node)
+        if libc.syscall(238, 1, C.byref(mask), 64) == 0:    # set_mempolicy(MPOL_PREFERRED, {node})
+            info["mempolicy"] = "MPOL_PREFERRED node %d" % node
+        else:
+            info["mempolicy"] = "set_mempolicy failed (errno %d)" % C.get_errno()
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = "%d cpus of node %d" % (len(allowed), node)
+    except Exception as e:
+        info["error"] = str(e)[:120]
+    return info
+
+
 # ------------------------------------------------------------------ GPU arm
 def gpu_arm(args):
     import torch
@@ -317,6 +351,7 @@ def gpu_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    placement = place_host_memory_near_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -564,6 +599,7 @@ def gpu_arm(args):
                            "max": float(per_step_ms.max()), "samples": int(per_step_ms.size), "what": "CUDA events around one batched cycle, rank 0"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * n * R * 8), "d2h_bytes_per_step": int(n * R * 8),
                     "steps": e2e_steps, "passes_ms": [round(x, 3) for x in e2e_runs], "checksum": checksum,
+                    "host_placement": placement,
                     "host_link": {"ms_per_step_copies_only": link_ms, "gbs": (3 * n * R * 8) / (link_ms * 1e-3) / 1e9,
                                   "e2e_fraction_of_link": link_ms / (e2e_ms / e2e_steps),
                                   "what": "the same %d + %d bytes per step as plain pinned cudaMemcpyAsync host->device and device->host on two "

@@ -51,7 +51,7 @@ def test_joint_task_with_internal_otg(robot_name):
     rb = RefBatch(robot_name, N, oriented=True); rb.set_state(q, dq)
     ojt = rb.add_jt(otg=True); rb.finalize()
     rng = np.random.default_rng(3)
-    K = 1000
+    K = 1300      # the last move (0.04 rad at >= 2 rad/s^2) lasts at most 0.29 s
     events = {0: "goal", 200: "goal", 330: "scaled", 500: "limits", 520: "goal", 700: "reinit", 760: "small_goal"}
     goal = q.copy()
     worst_des = worst_tau = 0.0
