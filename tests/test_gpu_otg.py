@@ -10,6 +10,13 @@ import pytest
 from oracle import sai_ref
 from tests.osc_testlib import REL_TOL, TASK_POINTS, rel_err, rot_exp, sample_states
 
+def tau_err(tau, ref):
+    """relative to the robot's torque scale, with an absolute floor: once a robot sits on its goal the commanded torque is the
+    rounding residue of (q - q_desired) times the gains (1e-12 Nm), and a ratio of two such numbers means nothing"""
+    scale = np.maximum(np.abs(ref).max(axis=1), 1e-3)
+    return (np.abs(tau - ref).max(axis=1) / scale).max()
+
+
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not sai_ref.available(oriented=True), reason="needs oracle/_ref/libsai_ref_orient.so")]
 
 
@@ -62,7 +69,7 @@ def test_joint_task_with_internal_otg(robot_name):
         elif ev == "scaled":
             goal = q + 1.4 * (goal - q)
         elif ev == "small_goal":      # short enough to be finished (and the goal flagged as reached) before the test ends
-            goal = q + rng.uniform(-0.04, 0.04, (N, n))
+            goal = jt.getDesiredPosition() + rng.uniform(-0.04, 0.04, (N, n))
         if ev in ("goal", "scaled", "small_goal"):
             jt.setGoalPosition(goal)
             for i in range(N):
@@ -80,7 +87,7 @@ def test_joint_task_with_internal_otg(robot_name):
         des = np.concatenate([jt.getDesiredPosition(), jt.getDesiredVelocity(), 1e-3 * jt.getDesiredAcceleration()], axis=1)
         odes = np.array([np.concatenate([t.getDesiredPosition(), t.getDesiredVelocity(), 1e-3 * t.getDesiredAcceleration()]) for t in ojt])
         worst_des = max(worst_des, np.abs(des - odes).max())
-        worst_tau = max(worst_tau, rel_err(tau, ref).max())
+        worst_tau = max(worst_tau, tau_err(tau, ref))
         assert worst_des < 1e-10 and worst_tau < REL_TOL, (k, worst_des, worst_tau)
         # the robots track the desired motion (a perfect inner loop): new state for the next cycle
         q_new = des[:, :n]; dq_new = des[:, n:2 * n]
@@ -141,7 +148,7 @@ def test_motion_force_task_with_internal_otg_in_the_flagship_hierarchy():
         odes = np.array([np.concatenate([t.getDesiredPosition(), t.getDesiredOrientation().reshape(-1), t.getDesiredLinearVelocity(), t.getDesiredAngularVelocity(),
                                          1e-3 * t.getDesiredLinearAcceleration(), 1e-3 * t.getDesiredAngularAcceleration()]) for t in omft])
         worst_des = max(worst_des, np.abs(des - odes).max())
-        worst_tau = max(worst_tau, rel_err(tau, ref).max())
+        worst_tau = max(worst_tau, tau_err(tau, ref))
         assert worst_des < 1e-9 and worst_tau < REL_TOL, (k, worst_des, worst_tau)
         assert (robot.status() & sp.capi.STATUS_UNHANDLED).sum() == 0
         q = q + 0.0005 * dq

@@ -573,7 +573,7 @@ def test_velocity_saturation_and_anisotropic_gains():
     with pytest.raises(ValueError):
         jt.enableVelocitySaturation(-0.1)             # JointTask.cpp:409-413
     with pytest.raises(NotImplementedError):
-        jt.enableInternalOtgAccelerationLimited(1.0, 2.0)
+        jt.enableInternalOtgJerkLimited(1.0, 2.0, 3.0)      # only the acceleration-limited generator is built (row f-4)
 
 
 def test_full_size_properties_262144_robots():
