@@ -487,6 +487,38 @@ def gpu_arm(args):
     multi_ms = 1e3 * (time.perf_counter() - t0)
     barrier()
 
+    # ---- the same hierarchy on UNFILTERED states (about half of the uniformly sampled Panda states sit inside the reference's
+    # singularity blending band and leave the fused kernel for the general path): reported as an extra so that the cost of
+    # that path is timed by the same run, not part of `value`
+    uq, udq, _, _ = sample_batch(sp, R, local_rank, min_ratio=0.0, shard=rank + 1000)
+    urobot = sp.BatchedRobot(ROBOT, R, device=local_rank)
+    urobot.setStream(stream.cuda_stream)
+    urobot.setQ(uq); urobot.setDq(udq); urobot.updateModel()
+    umft = sp.MotionForceTask(urobot, LINK, (np.eye(3), np.array(POINT))); ujt = sp.JointTask(urobot)
+    umft.disableInternalOtg(); ujt.disableInternalOtg()
+    uctrl = sp.RobotController(urobot, [umft, ujt])
+    ug = make_goals(rng, umft.getCurrentPosition(), umft.getCurrentOrientation(), uq)
+    umft.setGoalPosition(ug["xd"]); umft.setGoalOrientation(ug["Rd"]); umft.setGoalLinearVelocity(ug["vd"]); umft.setGoalAngularVelocity(ug["wd"])
+    ujt.setGoalPosition(ug["qd"])
+    ud = dict(robot=urobot, q=torch.from_numpy(np.ascontiguousarray(uq.T)).to(dev), dq=torch.from_numpy(np.ascontiguousarray(udq.T)).to(dev),
+              tau=torch.zeros((n, R), dtype=torch.float64, device=dev))
+    torch.cuda.set_stream(stream)
+    for _ in range(3):
+        step_device(ud)
+    barrier()
+    ue0, ue1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ue0.record()
+    for _ in range(30):
+        step_device(ud)
+    ue1.record()
+    barrier()
+    unfiltered_ms = ue0.elapsed_time(ue1) / 30
+    ust = urobot.status()
+    unfiltered_singular = float(((ust & capi.STATUS_SINGULAR_PATH) != 0).mean())
+    if (ust & capi.STATUS_UNHANDLED).any():
+        raise SystemExit("bench: unfiltered batch left the CUDA path")
+    urobot.close()
+
     # ---- end to end through the C ABI with pinned HOST buffers: every step copies q, dq host->device and tau
     # device->host inside the timed region.  The n_sets controller instances run on their own streams
     # (osc_step_async), so the copies of one instance overlap the kernels of the others; the region is closed by
@@ -557,9 +589,9 @@ def gpu_arm(args):
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([e2e_ms, multi_ms, link_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_ms, multi_ms, link_ms, unfiltered_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms, multi_ms, link_ms = float(t[0]), float(t[1]), float(t[2])
+        e2e_ms, multi_ms, link_ms, unfiltered_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     value = world * R * args.steps / (total_ms * 1e-3)
     e2e_value = world * R * e2e_steps / (e2e_ms * 1e-3)
 
@@ -605,7 +637,11 @@ def gpu_arm(args):
                                   "what": "the same %d + %d bytes per step as plain pinned cudaMemcpyAsync host->device and device->host on two "
                                           "streams at once, no kernel, max over ranks" % (2 * n * R * 8, n * R * 8)}},
             "extra": {"device_resident_one_stream_per_instance": {"value": world * R * multi_steps / (multi_ms * 1e-3), "unit": UNIT,
-                      "what": "same cycles, the %d controller instances on their own streams (independent batches overlap), host clock" % n_sets}},
+                      "what": "same cycles, the %d controller instances on their own streams (independent batches overlap), host clock" % n_sets},
+                      "unfiltered_states": {"value": world * R / (unfiltered_ms * 1e-3), "unit": UNIT, "ms_per_step": unfiltered_ms,
+                                            "robots_on_the_general_path": unfiltered_singular,
+                                            "what": "same hierarchy and batch size, uniformly sampled states without the s_min/s_max filter: the "
+                                                    "robots inside the reference's blending band take the general (SVD) path; 30 cycles, CUDA events"}},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",

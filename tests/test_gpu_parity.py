@@ -734,3 +734,49 @@ def test_task_observers_and_nullspaces(case):
     with pytest.raises(Exception):
         g.getUnitMassForce()
     robot.enableObservers(True)
+
+
+def test_config3_full_size_262144_robots_sampled_parity():
+    """BASELINE config 3 at its full size: 262,144 Pandas, partial MotionForceTask (XYZ) with force space
+    dimension 1 about Z, closed-loop force + POPC passivity, JointTask in the null space; 60 consecutive cycles with a noisy
+    sensed force and a drifting state.  Properties that do not need an oracle loop over the whole batch -- duplicated robots get
+    bit-identical torques and POPC state, no robot leaves the CUDA path -- plus a 2,048-robot sample against the CPU checker
+    (the C++ port, itself checked against the reference's compiled control law) at cycles 1, 50, 51 and 60."""
+    import sai_primitives_b200 as sp
+    from oracle.cpp_ref import CppOracleBatch
+    N, K, NS = 262144, 60, 2048
+    dirs = [(1, 0, 0), (0, 1, 0), (0, 0, 1)]
+    base_q, base_dq, _ = sample_states("panda", NS, min_sigma_ratio=0.1, dirs=np.eye(6)[:, :3])
+    rng = np.random.default_rng(12)
+    pick = rng.integers(0, NS, N); pick[:NS] = np.arange(NS)
+    q0, dq = base_q[pick], base_dq[pick]
+    link, pt = TASK_POINTS["panda"]
+    comp = (np.eye(3), np.array(pt))
+    robot = sp.BatchedRobot("panda", N)
+    robot.setQ(q0); robot.setDq(dq); robot.updateModel()
+    mft = sp.MotionForceTask(robot, link, comp, dirs, []); jt = sp.JointTask(robot)
+    ctrl = sp.RobotController(robot, [mft, jt])
+    assert mft.parametrizeForceMotionSpaces(1, (0, 0, 1)) is True
+    mft.setGoalForce(np.array([0, 0, -5.0])); mft.setClosedLoopForceControl(); mft.enablePassivity()
+    cb = CppOracleBatch("panda", NS); cb.set_state(base_q, base_dq)
+    tm = cb.add_mft(link, comp, dirs, []); cb.add_jt()
+    cb.mft_force_setup(tm, fdim=1, faxis=(0, 0, 1), cl_force=True, passivity=True)
+    cb.mft_set_force_goals(tm, np.tile([0, 0, -5.0], (NS, 1)), np.zeros((NS, 3)))
+    frng = np.random.default_rng(13)
+    for k in range(1, K + 1):
+        fs = np.array([0, 0, -5.0]) + frng.normal(0, 2.0, (NS, 3)); ms = frng.normal(0, 0.1, (NS, 3))
+        mft.updateSensedForceAndMoment(fs[pick], ms[pick]); cb.mft_update_sensed(tm, fs, ms)
+        ctrl.updateControllerTaskModels()
+        tau = ctrl.computeControlTorques()
+        ref = cb.cycle(n_threads=8)
+        if k in (1, 50, 51, K):
+            assert rel_err(tau[:NS], ref).max() < REL_TOL, k
+        qk = base_q + 0.0005 * k * base_dq
+        robot.setQ(qk[pick]); robot.updateModel(); cb.set_state(qk, base_dq)
+    st = robot.status()
+    assert (st & (sp.capi.STATUS_UNHANDLED | sp.capi.STATUS_POPC_OVERFLOW)).sum() == 0 and np.isfinite(tau).all()
+    popc = mft._get(sp.capi.MFT_POPC_STATE)
+    first = {}
+    for i in range(NS, N, 499):            # duplicates of a sampled robot: bit-identical torques and passivity state
+        j = int(pick[i])
+        assert np.array_equal(tau[i], tau[j]) and np.array_equal(popc[i], popc[j])
