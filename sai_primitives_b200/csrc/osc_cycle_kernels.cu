@@ -64,12 +64,13 @@ static bool cycle_spec_eligible(const OscProgram& P, bool has_jt, bool* motion) 
 	}
 	const DevMft& t = P.mft[0];
 	const osc_mft_params& p = t.p;
-	if (p.use_velocity_saturation || p.dynamic_decoupling_type == OSC_IMPEDANCE) return false;
+	// IMPEDANCE decoupling needs no code of its own (Lambda_modified = I: the solves are skipped); velocity saturation of the
+	// motion-force task is part of the general control law, which the structural specialisation (MOTION = false) keeps
 	*motion = t.full && p.force_space_dimension == 0 && p.moment_space_dimension == 0 && !p.closed_loop_force_control &&
-			  !p.closed_loop_moment_control;
+			  !p.closed_loop_moment_control && !p.use_velocity_saturation;
 	if (has_jt) {
 		const DevJt& j = P.jt[0];
-		if (!j.full || j.p.use_velocity_saturation || j.p.dynamic_decoupling_type == OSC_IMPEDANCE) return false;
+		if (!j.full || j.p.use_velocity_saturation) return false;  // the staged joint control law has no velocity saturation
 	}
 	return true;
 }
@@ -152,15 +153,15 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 			e0 = launch_variant<N, R, JT, false>(P, stream);
 		else if (spec && motion)
 			e0 = P.gravity_comp ? launch_variant<N, R, JT, true, true, true>(P, stream) : launch_variant<N, R, JT, true, true, false>(P, stream);
-		else if (spec && !P.gravity_comp)
-			e0 = launch_variant<N, R, JT, true, true, false, false>(P, stream);  // full task with force / moment control
+		else if (spec)	// full task with force / moment control or velocity saturation
+			e0 = P.gravity_comp ? launch_variant<N, R, JT, true, true, true, false>(P, stream) : launch_variant<N, R, JT, true, true, false, false>(P, stream);
 		else
 			e0 = launch_variant<N, R, JT, true>(P, stream);
 	} else if constexpr (R == 3) {
 		// the other common shape: three controlled directions (position only, or a planar task), any control law
 		bool motion = false;
-		if (cycle_spec_eligible(P, JT, &motion) && !P.gravity_comp)
-			e0 = launch_variant<N, R, JT, false, true, false, false>(P, stream);
+		if (cycle_spec_eligible(P, JT, &motion))
+			e0 = P.gravity_comp ? launch_variant<N, R, JT, false, true, true, false>(P, stream) : launch_variant<N, R, JT, false, true, false, false>(P, stream);
 		else
 			e0 = launch_variant<N, R, JT, false>(P, stream);
 	} else {
