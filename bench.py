@@ -50,6 +50,16 @@ MIN_PASSES = 5
 LATENCY_SAMPLES = 1000        # >= 1000 single-cycle brackets for the percentiles
 
 
+def workload_config(args, world):
+    """`config` of the JSON line: the definition of the workload, identical for both arms (measured properties of the
+    sampled inputs go under `inputs`)"""
+    R = args.robots
+    return {"workload": WORKLOAD, "robots_per_gpu": R, "robots_total": R * world,
+            "state_filter": "uniform joint states, rejected while s_min/s_max < %.3g (SURVEY.md 8d)" % args.min_ratio,
+            "l2": "inputs larger than L2: %d controller instances (%.0f MB of state) used round-robin" % (args.sets, args.sets * R * 8 * 250 / 1e6),
+            "parallelism": "robots sharded by batch index, one process per GPU, no collective"}
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -278,8 +288,8 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "robots_per_gpu": args.robots, "robots_total": args.robots,
-                   "state_filter": "s_min/s_max >= %.3g, rejected fraction %.3f" % (args.min_ratio, rejected)},
+        "config": workload_config(args, max(1, args.gpus)),
+        "inputs": {"rejected_fraction": rejected, "what": "one rank's shard (%d robots per step) on the host cores" % args.robots},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cc.threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -618,11 +628,8 @@ def gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "robots_per_gpu": R, "robots_total": R * world,
-                       "l2": "inputs larger than L2: %d controller instances (%.0f MB of state) used round-robin" % (n_sets, n_sets * R * 8 * 250 / 1e6),
-                       "state_filter": "s_min/s_max >= %.3g, rejected fraction %.3f; robots on the general (SVD) path: %.4f" % (args.min_ratio, rejected, singular_fraction),
-                       "parallelism": "robots sharded by batch index, %d process(es), no collective" % world},
+            "config": workload_config(args, world),
+            "inputs": {"rejected_fraction": rejected, "robots_on_the_general_path": singular_fraction},
             "timing": {"brackets": int(pass_ms.size), "bracket_ms_median": total_ms, "bracket_ms_min": float(pass_ms.min()),
                        "bracket_ms_max": float(pass_ms.max()), "timed_ms_total": float(pass_ms.sum()),
                        "what": "each bracket = --steps back-to-back cycles between two CUDA events with barrier + synchronize on both sides; "
