@@ -356,6 +356,11 @@ int64_t osc_launch_count(const osc_handle* h);
 int osc_debug_popc_sequence(osc_handle* h, int task_id, int n_steps, const double* fd, const double* fs, const double* vcl,
 							const double* vr, double kv_force, double kff_force, double* out);
 
+/* ---- measurement aid (no reference counterpart): %globaltimer stamps of every block of the fused kernel over the last 8 cycles,
+ * so that the overlap of consecutive cycles can be looked at (tools/pipeline_trace.py).  out == NULL: switch the stamps on / off;
+ * out != NULL: read back [cycle & 7][block][start, end] (nanoseconds).  Returns the number of blocks per cycle. ---- */
+int osc_debug_block_times(osc_handle* h, int enabled, unsigned long long* out, int64_t out_capacity);
+
 /* ---- measurement aid (no reference counterpart): sustained FP64 FMA rate of the device in TFLOP/s, from a DFMA-only
  * kernel run for about `seconds` (bench.py reports the roofline against it next to the datasheet figure) ---- */
 int osc_measure_fp64_peak(osc_handle* h, double seconds, double* tflops_out);

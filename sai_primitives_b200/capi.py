@@ -212,6 +212,7 @@ SYMBOLS = {
     "osc_world_register_robot": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(D)]),
     "osc_debug_popc_sequence": (C.c_int, [_H, C.c_int, C.c_int, _PD, _PD, _PD, _PD, C.c_double, C.c_double, _PD]),
     "osc_measure_fp64_peak": (C.c_int, [_H, C.c_double, _PD]),
+    "osc_debug_block_times": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
     "osc_sim_integrate": (C.c_int, [_H, _PD, _PD, _PD, C.c_double, C.c_int, C.c_int]),
     "osc_eval_model": (C.c_int, [_H, C.c_int, C.POINTER(LinkFrame), C.POINTER(D), _PD, _PD, _PD, _PD, _PD, C.c_int]),
 }

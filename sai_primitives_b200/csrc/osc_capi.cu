@@ -48,6 +48,7 @@ struct osc_handle {
 	int32_t *d_sing_list = nullptr, *d_sing_count = nullptr;
 	// cycle pipelining (osc_pipeline.cuh): per-block cycle numbers, general-path completion word, mapped host word
 	uint32_t *d_block_epoch = nullptr, *d_general_done = nullptr;
+	unsigned long long* d_block_times = nullptr;  // osc_debug_block_times
 	int otg_tasks = 0;			  // tasks whose internal OTG is on
 	double* d_sim = nullptr;	  // staging of osc_sim_integrate with host buffers (q, dq, tau)
 	double* d_scratch = nullptr;  // output of the on-request observers (osc_observers.cuh)
@@ -1132,6 +1133,25 @@ int osc_enable_joint_limit_avoidance(osc_handle* h, int enabled) {
 	ENTER(h);
 	h->jla_enabled = enabled != 0;
 	return OSC_OK;
+}
+
+int osc_debug_block_times(osc_handle* h, int enabled, unsigned long long* out, int64_t out_capacity) {
+	ENTER(h);
+	const size_t blocks = ((size_t)h->NR + osc::kCycleBlock - 1) / osc::kCycleBlock;
+	const size_t words = blocks * 8 * 2;
+	if (out) {	// read back: [cycle & 7][block][start, end] in globaltimer nanoseconds
+		if (!h->d_block_times) return fail(h, OSC_ERR_STATE, "block times were not enabled");
+		if (out_capacity < (int64_t)words) return fail(h, OSC_ERR_INVALID_ARGUMENT, "output too small");
+		CUDA_TRY(h, cudaMemcpyAsync(out, h->d_block_times, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+		CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+		return (int)blocks;
+	}
+	if (enabled && !h->d_block_times) {
+		int rc = dev_alloc(h, &h->d_block_times, words, true);
+		if (rc != OSC_OK) return rc;
+	}
+	h->prog.block_times = enabled ? h->d_block_times : nullptr;
+	return (int)blocks;
 }
 
 int osc_enable_observers(osc_handle* h, int enabled) {

@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 	prefetch_block_rows<N, R, HAS_JT>(P, blockIdx.x);
 #endif
 	grid_dependency_wait(P);
+	stamp_block(P, 0);
 	if (!P.block_epoch && i_raw == 0 && P.sing_count) P.sing_count[P.sing_parity ^ 1] = 0;
 	bool handed_over = false;
 	double q[N];
@@ -771,6 +772,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 		P.status[i] = status;
 	}
 	publish_cycle(P, handed_over);
+	stamp_block(P, 1);
 }
 
 }  // namespace osc

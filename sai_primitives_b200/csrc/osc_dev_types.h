@@ -150,5 +150,6 @@ struct OscProgram {
 	uint32_t* general_done;	 // [0] cycle number the general-path kernel has completed, [1] its block completion counter, [2] count last sent to host_seen
 	int32_t* host_seen;		 // mapped host word: hand-over count of the last completed cycle (a scheduling hint for the host)
 	uint32_t epoch;			 // cycle number of this launch (31 bits used)
+	unsigned long long* block_times;  // measurement aid (osc_debug_block_times): globaltimer at block start / end, 8 cycles deep; normally null
 	int32_t general_grid_small;	 // host hint: the last cycles handed nothing over, a handful of general-path blocks is enough
 };

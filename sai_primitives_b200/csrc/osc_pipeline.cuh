@@ -39,6 +39,14 @@ DEVI void wait_previous_cycle(const OscProgram& P) {
 	}
 	__syncwarp();
 }
+// measurement aid: nanosecond timestamps of every block of the last 8 cycles (tools/pipeline_trace.py)
+DEVI void stamp_block(const OscProgram& P, int which) {
+	if (P.block_times && threadIdx.x == 0) {
+		unsigned long long t;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+		P.block_times[((size_t)(P.epoch & 7u) * gridDim.x + blockIdx.x) * 2 + which] = t;
+	}
+}
 DEVI void grid_dependency_wait(const OscProgram& P) {
 	if (!P.block_epoch) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
