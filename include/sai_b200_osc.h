@@ -361,6 +361,12 @@ int osc_debug_popc_sequence(osc_handle* h, int task_id, int n_steps, const doubl
  * out != NULL: read back [cycle & 7][block][start, end] (nanoseconds).  Returns the number of blocks per cycle. ---- */
 int osc_debug_block_times(osc_handle* h, int enabled, unsigned long long* out, int64_t out_capacity);
 
+/* ---- measurement aid (no reference counterpart): how the last cycle that took the split blending path (many robots inside the
+ * reference's singularity band, SingularityHandler.cpp:75-368) distributed them: out4 = robots with 0, 1 and 2 singular
+ * directions handled by the blending kernels, and robots sent on to the rolled general path.  -1 four times when the handle
+ * has not used that path. ---- */
+int osc_debug_general_path_counts(osc_handle* h, int32_t* out4);
+
 /* ---- measurement aid (no reference counterpart): sustained FP64 FMA rate of the device in TFLOP/s, from a DFMA-only
  * kernel run for about `seconds` (bench.py reports the roofline against it next to the datasheet figure) ---- */
 int osc_measure_fp64_peak(osc_handle* h, double seconds, double* tflops_out);

@@ -213,6 +213,7 @@ SYMBOLS = {
     "osc_debug_popc_sequence": (C.c_int, [_H, C.c_int, C.c_int, _PD, _PD, _PD, _PD, C.c_double, C.c_double, _PD]),
     "osc_measure_fp64_peak": (C.c_int, [_H, C.c_double, _PD]),
     "osc_debug_block_times": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
+    "osc_debug_general_path_counts": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "osc_sim_integrate": (C.c_int, [_H, _PD, _PD, _PD, C.c_double, C.c_int, C.c_int]),
     "osc_eval_model": (C.c_int, [_H, C.c_int, C.POINTER(LinkFrame), C.POINTER(D), _PD, _PD, _PD, _PD, _PD, C.c_int]),
 }

@@ -8,7 +8,7 @@
 // (src/tasks/SingularityHandler.cpp:75-368) and JointTask with the resulting null space (src/tasks/JointTask.cpp:218-356).
 //
 // Algebra (same whitening as the fast path).  With M = L L^T, X = L^-1 J^T (n x 6) and the
-// eigen-decomposition J J^T = U S^2 U^T (cyclic Jacobi on the 6 x 6 Gram matrix):
+// eigen-decomposition J J^T = U S^2 U^T (6 x 6 Gram matrix: tridiagonalisation + implicit QL, osc_eig6.h):
 //   U = [U_ns | U_s] (first NNS / last NS columns),  V_s = J^T U_s S_s^-1 = L X U_s S_s^-1
 //   X U = Q R' (Householder):  J_ns M^-1 J_ns^T = R'_11^T R'_11,   J_s M^-1 J_s^T = R'_12^T R'_12 + R'_22^T R'_22,
 //   posture Jacobian J_post = V_s^T N_ns:  L^-1 J_post^T = Q [0; R'_22; 0] S_s^-1,  so
@@ -18,83 +18,10 @@
 #include "osc_kindyn.cuh"
 #include "osc_singular.cuh"
 #include "osc_tasks.cuh"
+#define OSC_EIG6_LEAN_MATH
+#include "osc_eig6.h"
 
 namespace osc {
-
-// Jacobi eigen-decomposition of a symmetric 6 x 6 matrix held in registers: G -> diag(lambda), U <- eigenvectors (columns).
-// Parallel (round-robin) ordering: a sweep is five rounds of three rotations on disjoint index pairs.  The three rotation
-// angles of a round come from the same matrix, so their scalar chains (reciprocal, two square roots: ~30 dependent FP64
-// operations each) overlap instead of following one another, and the rotations are branch-free (c = 1, s = 0 where the
-// off-diagonal entry is already negligible): no divergence inside a sweep.  The sweep loop is per thread (warp
-// divergence = the slowest lane).
-template <int P, int Q>
-DEVI void jacobi_angle(const double (&G)[6][6], double& c, double& s) {
-	const double gpq = G[P][Q];
-	const bool rot = fabs(gpq) > 1e-18 * (fabs(G[P][P]) + fabs(G[Q][Q]));
-	const double g = rot ? gpq : 1.0;
-	// lean reciprocal / square roots (osc_math.cuh): g is non-zero and both radicands are >= 1
-	const double theta = (G[Q][Q] - G[P][P]) * (0.5 * rcp_nz(g));
-	const double t = (theta >= 0.0 ? 1.0 : -1.0) * rcp_nz(fabs(theta) + sqrt_pos(theta * theta + 1.0));
-	const double cc = rsqrt_pos(t * t + 1.0);
-	c = rot ? cc : 1.0;
-	s = rot ? t * cc : 0.0;
-}
-template <int P, int Q>
-DEVI void jacobi_cols(double (&A)[6][6], double c, double s) {	// A <- A J(P, Q)
-#pragma unroll
-	for (int k = 0; k < 6; k++) {
-		const double akp = A[k][P], akq = A[k][Q];
-		A[k][P] = c * akp - s * akq;
-		A[k][Q] = s * akp + c * akq;
-	}
-}
-template <int P, int Q>
-DEVI void jacobi_rows(double (&A)[6][6], double c, double s) {	// A <- J(P, Q)^T A
-#pragma unroll
-	for (int k = 0; k < 6; k++) {
-		const double apk = A[P][k], aqk = A[Q][k];
-		A[P][k] = c * apk - s * aqk;
-		A[Q][k] = s * apk + c * aqk;
-	}
-}
-template <int P0, int Q0, int P1, int Q1, int P2, int Q2>
-DEVI void jacobi_round(double (&G)[6][6], double (&U)[6][6]) {
-	double c0, s0, c1, s1, c2, s2;
-	jacobi_angle<P0, Q0>(G, c0, s0);
-	jacobi_angle<P1, Q1>(G, c1, s1);
-	jacobi_angle<P2, Q2>(G, c2, s2);
-	jacobi_cols<P0, Q0>(G, c0, s0);
-	jacobi_cols<P1, Q1>(G, c1, s1);
-	jacobi_cols<P2, Q2>(G, c2, s2);
-	jacobi_rows<P0, Q0>(G, c0, s0);
-	jacobi_rows<P1, Q1>(G, c1, s1);
-	jacobi_rows<P2, Q2>(G, c2, s2);
-	jacobi_cols<P0, Q0>(U, c0, s0);
-	jacobi_cols<P1, Q1>(U, c1, s1);
-	jacobi_cols<P2, Q2>(U, c2, s2);
-}
-DEVI void jacobi_eig6(double (&G)[6][6], double (&U)[6][6]) {
-#pragma unroll
-	for (int a = 0; a < 6; a++)
-#pragma unroll
-		for (int b = 0; b < 6; b++) U[a][b] = (a == b) ? 1.0 : 0.0;
-	for (int sweep = 0; sweep < 30; sweep++) {
-		double off = 0.0, dia = 0.0;
-#pragma unroll
-		for (int a = 0; a < 6; a++) {
-			dia += G[a][a] * G[a][a];
-#pragma unroll
-			for (int b = 0; b < a; b++) off += G[a][b] * G[a][b];
-		}
-		// off-diagonal entries at 1e-15 of the diagonal scale: the rounding floor of the rotations is ~1e-16
-		if (off <= 1e-30 * dia) break;
-		jacobi_round<0, 5, 1, 4, 2, 3>(G, U);
-		jacobi_round<0, 4, 3, 5, 1, 2>(G, U);
-		jacobi_round<0, 3, 2, 4, 1, 5>(G, U);
-		jacobi_round<0, 2, 1, 3, 4, 5>(G, U);
-		jacobi_round<0, 1, 2, 5, 3, 4>(G, U);
-	}
-}
 
 // (A - delta z z^T / kappa)^-1 y for A = Rb^T Rb given by its upper-triangular factor stored in T[C0 + i][C0 + j] (i <= j),
 // size S; rinv = reciprocal diagonal.  use_sm = false gives plain A^-1 y.
@@ -135,12 +62,44 @@ DEVI void solve_block_sm(const double (&T)[N][6], const double (&rinv)[6], doubl
 	}
 }
 
+// Where blend_path reads the results of the first half from: the registers of the same thread (osc_blend_kernel) or the
+// scratch block of the split path (BlendLayout below), element by element at the point of use -- the 150 doubles of L, J, X
+// and U are then never live at the same time as the control law and the classification, which is what spilled.
+template <int N>
+struct BlendRegisterSource {
+	const double (&grav_)[N];
+	const double (&L_)[N][N];
+	const double (&invd_)[N];
+	const double (&Mdiag_)[N];
+	const double (&JT0_)[N][6];
+	const double (&U_)[6][6];
+	DEVI double grav(int j) const { return grav_[j]; }
+	DEVI double l(int r, int c) const { return L_[r][c]; }
+	DEVI double invd(int r) const { return invd_[r]; }
+	DEVI double mdiag(int r) const { return Mdiag_[r]; }
+	DEVI double jt0(int j, int a) const { return JT0_[j][a]; }
+	DEVI double u(int a, int c) const { return U_[a][c]; }
+};
+template <int N>
+struct BlendScratchSource {
+	using BL = BlendLayout<N>;
+	const double* S;  // scratch + slot
+	int64_t cap;
+	DEVI double at(int c) const { return S[(int64_t)c * cap]; }
+	DEVI double grav(int j) const { return at(BL::GRAV + j); }
+	DEVI double l(int r, int c) const { return at(BL::LL + r * (r + 1) / 2 + c); }
+	DEVI double invd(int r) const { return at(BL::INVD + r); }
+	DEVI double mdiag(int r) const { return at(BL::MDIAG + r); }
+	DEVI double jt0(int j, int a) const { return at(BL::JT0 + j * 6 + a); }
+	DEVI double u(int a, int c) const { return at(BL::U + a * 6 + c); }
+};
+
 // Everything after the eigen-decomposition, for NS singular directions (NS = 0: the thin band of non-singular robots
 // the sound test of the fast kernel rejects).  Returns false when the case must go to the general path.
-template <int N, int NS, bool HAS_JT>
-DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const double (&dq)[N], KinDyn<N>& kd, const double (&L)[N][N],
-					 const double (&invd)[N], const double (&Mdiag)[N], const double (&JT0)[N][6], const double (&Xw)[N][6],
-					 const double (&U)[6][6], const double (&sig)[6], double alpha, const double x[3], const double Rc[9], uint32_t status) {
+// MOTION: the task is under pure motion control (host check, as for the fused kernel): only the two PID laws are compiled in and F = 0.
+template <int N, int NS, bool HAS_JT, class Src, bool MOTION = false>
+DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const double (&dq)[N], const Src& src, const double (&sig)[6], double alpha,
+					 const double x[3], const double Rc[9], uint32_t status) {
 	constexpr int NNS = 6 - NS;
 	const int64_t NR = P.n_robots;
 	const DevModel& mdl = P.model;
@@ -151,46 +110,35 @@ DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const
 	const int dec = p.dynamic_decoupling_type;
 
 	// bounded inertia: one clamped entry -> rank-one (Sherman-Morrison); several -> general path
-	double dclamp[N], delta = 0.0, mu = 0.0, g[N];
+	double delta = 0.0;
 	int kclamp = 0;
 	if (dec == OSC_BOUNDED_INERTIA_ESTIMATES) {
 #pragma unroll
 		for (int j = 0; j < N; j++) {
-			const double dj = p.bie_threshold - Mdiag[j];
-			dclamp[j] = (dj > 0.0) ? dj : 0.0;
-			delta += dclamp[j];
+			const double dj = p.bie_threshold - src.mdiag(j);
+			delta += (dj > 0.0) ? dj : 0.0;
 			kclamp += (dj > 0.0) ? 1 : 0;
 		}
 		if (kclamp >= 2) return false;
 	}
 	const bool sm = (dec == OSC_BOUNDED_INERTIA_ESTIMATES) && kclamp == 1;
-	if (sm) {
-#pragma unroll
-		for (int j = 0; j < N; j++) g[j] = (dclamp[j] > 0.0) ? 1.0 : 0.0;
-		solve_lower<N>(L, invd, g);
-#pragma unroll
-		for (int j = 0; j < N; j++) mu += g[j] * g[j];
-	}
-	const double kappa = 1.0 + delta * mu;
 
 	// right singular vectors of the singular directions: V_s = J^T U_s / sigma, oriented so that the largest-magnitude
 	// entry is positive (sign convention of this repo); the matching U_s column follows the sign
 	double Us[6][NS > 0 ? NS : 1], Vs[N][NS > 0 ? NS : 1];
-	double Ue[6][6];  // [U_ns | U_s] with the final signs
-#pragma unroll
-	for (int a = 0; a < 6; a++)
-#pragma unroll
-		for (int c = 0; c < 6; c++) Ue[a][c] = U[a][c];
+	double sgn_s[NS > 0 ? NS : 1];	// [U_ns | U_s] with the final signs is  src.u(a, c) * (c < NNS ? 1 : sgn_s[c - NNS])
 	if constexpr (NS > 0) {
 #pragma unroll
 		for (int c = 0; c < NS; c++) {
 			double vmax = 0.0, amax = -1.0;
 			const double inv = 1.0 / sig[NNS + c];
 #pragma unroll
+			for (int a = 0; a < 6; a++) Us[a][c] = src.u(a, NNS + c);
+#pragma unroll
 			for (int j = 0; j < N; j++) {
 				double s = 0.0;
 #pragma unroll
-				for (int a = 0; a < 6; a++) s += JT0[j][a] * U[a][NNS + c];
+				for (int a = 0; a < 6; a++) s += src.jt0(j, a) * Us[a][c];
 				s *= inv;
 				Vs[j][c] = s;
 				if (fabs(s) > amax) {
@@ -199,47 +147,23 @@ DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const
 				}
 			}
 			const double sgn = (vmax < 0.0) ? -1.0 : 1.0;
+			sgn_s[c] = sgn;
 #pragma unroll
 			for (int j = 0; j < N; j++) Vs[j][c] *= sgn;
 #pragma unroll
-			for (int a = 0; a < 6; a++) {
-				Us[a][c] = sgn * U[a][NNS + c];
-				Ue[a][NNS + c] = Us[a][c];
-			}
+			for (int a = 0; a < 6; a++) Us[a][c] = sgn * Us[a][c];
 		}
 	}
 
-	// task velocity J0 dq (the Jacobian is not needed after this point)
+	// task velocity J0 dq
 	double v[3] = {0, 0, 0}, w[3] = {0, 0, 0};
 #pragma unroll
 	for (int j = 0; j < N; j++)
 #pragma unroll
 		for (int k = 0; k < 3; k++) {
-			v[k] += JT0[j][k] * dq[j];
-			w[k] += JT0[j][3 + k] * dq[j];
+			v[k] += src.jt0(j, k) * dq[j];
+			w[k] += src.jt0(j, 3 + k) * dq[j];
 		}
-	// ---- T = X U (its Householder QR follows below; X is not needed after this point)
-	double T[N][6];
-#pragma unroll
-	for (int r = 0; r < N; r++)
-#pragma unroll
-		for (int c = 0; c < 6; c++) {
-			double s = 0.0;
-#pragma unroll
-			for (int a = 0; a < 6; a++) s += Xw[r][a] * Ue[a][c];
-			T[r][c] = s;
-		}
-	// z = (X U)^T g for the bounded-inertia rank-one update, before T is overwritten
-	double zu[6];
-#pragma unroll
-	for (int c = 0; c < 6; c++) {
-		double s = 0.0;
-		if (sm) {
-#pragma unroll
-			for (int r = 0; r < N; r++) s += T[r][c] * g[r];
-		}
-		zu[c] = s;
-	}
 
 	// ---- classifySingularity (:230-295): memory of the handler
 	int32_t c1 = ist[(int64_t)MI_T1_COUNTER * NR + i], c2 = ist[(int64_t)MI_T2_COUNTER * NR + i];
@@ -314,24 +238,74 @@ DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const
 
 	// ---- control law (state update happens exactly once, here)
 	double fstar[6], F[6];
-	mft_control_law(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status);
+	mft_control_law<MOTION>(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status);
 
+	// dynamics factor (read only now: nothing above needs it), and the unit vector of the clamped entry through it
+	double L[N][N], invd[N], g[N], mu = 0.0;
+#pragma unroll
+	for (int r = 0; r < N; r++) {
+		invd[r] = src.invd(r);
+#pragma unroll
+		for (int c = 0; c < N; c++) L[r][c] = (c <= r) ? src.l(r, c <= r ? c : 0) : 0.0;
+	}
+	if (sm) {
+#pragma unroll
+		for (int j = 0; j < N; j++) g[j] = (p.bie_threshold - src.mdiag(j) > 0.0) ? 1.0 : 0.0;
+		solve_lower<N>(L, invd, g);
+#pragma unroll
+		for (int j = 0; j < N; j++) mu += g[j] * g[j];
+	}
+	const double kappa = 1.0 + delta * mu;
+	// ---- T = X U with X = L^-1 J^T (its Householder QR follows), and the coordinates of f*, F in the rotated task basis
+	double T[N][6], au[6], bu[6];
+	{
+		double Ue[6][6];
+#pragma unroll
+		for (int a = 0; a < 6; a++)
+#pragma unroll
+			for (int c = 0; c < 6; c++) Ue[a][c] = (NS > 0 && c >= NNS) ? sgn_s[c >= NNS ? c - NNS : 0] * src.u(a, c) : src.u(a, c);
+#pragma unroll
+		for (int c = 0; c < 6; c++) {
+			double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+			for (int a = 0; a < 6; a++) {
+				s1 += Ue[a][c] * fstar[a];
+				s2 += Ue[a][c] * F[a];
+			}
+			au[c] = s1;
+			bu[c] = s2;
+		}
+		// T = X U = L^-1 (J^T U): row r of J^T U, then the forward substitution with the rows above it
+#pragma unroll
+		for (int r = 0; r < N; r++) {
+			double jr[6];
+#pragma unroll
+			for (int a = 0; a < 6; a++) jr[a] = src.jt0(r, a);
+#pragma unroll
+			for (int c = 0; c < 6; c++) {
+				double s = 0.0;
+#pragma unroll
+				for (int a = 0; a < 6; a++) s += jr[a] * Ue[a][c];
+#pragma unroll
+				for (int k = 0; k < r; k++) s -= L[r][k] * T[k][c];
+				T[r][c] = s * invd[r];
+			}
+		}
+	}
+	// z = (X U)^T g for the bounded-inertia rank-one update, before T is overwritten
+	double zu[6];
+#pragma unroll
+	for (int c = 0; c < 6; c++) {
+		double s = 0.0;
+		if (sm) {
+#pragma unroll
+			for (int r = 0; r < N; r++) s += T[r][c] * g[r];
+		}
+		zu[c] = s;
+	}
 	double vhead[6], beta[6], rinv[6];
 	householder_qr<N, 6, 0>(T, vhead, beta, rinv);
 
-	// coordinates of f*, F in the rotated task basis
-	double au[6], bu[6];
-#pragma unroll
-	for (int c = 0; c < 6; c++) {
-		double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-		for (int a = 0; a < 6; a++) {
-			s1 += Ue[a][c] * fstar[a];
-			s2 += Ue[a][c] * F[a];
-		}
-		au[c] = s1;
-		bu[c] = s2;
-	}
 	const bool types_nonempty = (n_types != 0);
 	const bool impedance_plain = types_nonempty && dec == OSC_IMPEDANCE;
 
@@ -603,7 +577,7 @@ DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const
 				int kj = 0;
 #pragma unroll
 				for (int j = 0; j < N; j++) {
-					const double d = jp.bie_threshold - Mdiag[j];
+					const double d = jp.bie_threshold - src.mdiag(j);
 					gj[j] = (d > 0.0) ? 1.0 : 0.0;
 					dj += (d > 0.0) ? d : 0.0;
 					kj += (d > 0.0) ? 1 : 0;
@@ -645,7 +619,7 @@ DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const
 	}
 	if (P.gravity_comp) {
 #pragma unroll
-		for (int j = 0; j < N; j++) tau[j] += kd.g[j];
+		for (int j = 0; j < N; j++) tau[j] += src.grav(j);
 	}
 	if (status & OSC_STATUS_UNHANDLED) {
 #pragma unroll
@@ -694,11 +668,9 @@ DEVI bool blend_robot(const OscProgram& P, const int64_t i) {
 			G[a][b] = s;
 			G[b][a] = s;
 		}
-	jacobi_eig6(G, U);
 	// sort eigenpairs by decreasing eigenvalue (selection by compare-exchange: static register indices only)
 	double lam[6];
-#pragma unroll
-	for (int a = 0; a < 6; a++) lam[a] = G[a][a];
+	sym_eig6(G, U, lam);
 #pragma unroll
 	for (int a = 0; a < 5; a++)
 #pragma unroll
@@ -744,7 +716,7 @@ DEVI bool blend_robot(const OscProgram& P, const int64_t i) {
 		if (n_s > 0 && !p.singularity_handling_enabled) return false;
 	}
 
-	// dynamics factor and whitened Jacobian
+	// dynamics factor
 	double Mdiag[N], invd[N], L[N][N];
 #pragma unroll
 	for (int r = 0; r < N; r++) {
@@ -753,19 +725,10 @@ DEVI bool blend_robot(const OscProgram& P, const int64_t i) {
 		for (int c = 0; c <= r; c++) L[r][c] = kd.M[r][c];
 	}
 	cholesky_lower<N>(L, invd);
-	double Xw[N][6];
-#pragma unroll
-	for (int r = 0; r < N; r++)
-#pragma unroll
-		for (int a = 0; a < 6; a++) {
-			double s = JT0[r][a];
-#pragma unroll
-			for (int k = 0; k < r; k++) s -= L[r][k] * Xw[k][a];
-			Xw[r][a] = s * invd[r];
-		}
-	if (n_s == 0) return blend_path<N, 0, HAS_JT>(P, i, q, dq, kd, L, invd, Mdiag, JT0, Xw, U, sig, alpha, x, Rc, OSC_STATUS_SINGULAR_PATH);
-	if (n_s == 1) return blend_path<N, 1, HAS_JT>(P, i, q, dq, kd, L, invd, Mdiag, JT0, Xw, U, sig, alpha, x, Rc, OSC_STATUS_SINGULAR_PATH);
-	return blend_path<N, 2, HAS_JT>(P, i, q, dq, kd, L, invd, Mdiag, JT0, Xw, U, sig, alpha, x, Rc, OSC_STATUS_SINGULAR_PATH);
+	const BlendRegisterSource<N> src{kd.g, L, invd, Mdiag, JT0, U};
+	if (n_s == 0) return blend_path<N, 0, HAS_JT>(P, i, q, dq, src, sig, alpha, x, Rc, OSC_STATUS_SINGULAR_PATH);
+	if (n_s == 1) return blend_path<N, 1, HAS_JT>(P, i, q, dq, src, sig, alpha, x, Rc, OSC_STATUS_SINGULAR_PATH);
+	return blend_path<N, 2, HAS_JT>(P, i, q, dq, src, sig, alpha, x, Rc, OSC_STATUS_SINGULAR_PATH);
 }
 
 // Hand-over list of the fast kernel for the flagship hierarchy: unrolled blending path, general path as fallback.
@@ -781,6 +744,206 @@ __global__ void __launch_bounds__(64) osc_blend_kernel(const __grid_constant__ O
 		if (!blend_robot<N, HAS_JT>(P, i)) generic_cycle_one<N>(P, i, OSC_STATUS_SINGULAR_PATH);
 	}
 	publish_general_done(P, count);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// The same path split over kernels, for cycles in which the host hint (osc_pipeline.cuh) says that many robots are on the
+// general path.  osc_blend_kernel above recomputes kinematics and dynamics, and walks the eigen-decomposition and up to
+// three inlined variants (0 / 1 / 2 singular directions) in one 1 MB instruction stream; a warp with mixed robots walks
+// the variants one after the other.  Here
+//   0. the fused kernel parks what it had already computed when it decided to hand the robot over (pose, M = L L^T, the
+//      Jacobian: park_for_blend, osc_cycle.cuh) in a scratch block, component c of list slot s at
+//      scratch[c * cap + s];
+//   1. osc_blend_classify_kernel does the eigen-decomposition and the classification and appends the slot to the list of
+//      its variant (warp-aggregated atomics: runs of consecutive slots);
+//   2. osc_blend_variants_kernel deals the three lists to its blocks chunk by chunk, so that a warp only ever executes one
+//      variant, reading the parked state element by element where blend_path uses it;
+//   3. osc_blend_fallback_kernel takes what the blending path does not specialise through the rolled general path and
+//      publishes the end of the cycle's general path.
+// Classification of list slot `slot` from what the fused kernel parked there: returns the variant (number of singular
+// directions, 0..2) or 3 when the robot needs the general path (the tests of blend_robot, in the same order).
+template <int N, bool HAS_JT>
+DEVI int blend_classify(const OscProgram& P, const int64_t slot) {
+	using BL = BlendLayout<N>;
+	const int64_t cap = P.blend_cap;
+	double* S = P.blend_scratch + slot;
+	const DevMft& t = P.mft[0];
+	const osc_mft_params& p = t.p;
+	if (!t.full || t.rank != 6) return 3;
+	if (HAS_JT && p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES && P.jt[0].p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES &&
+		P.jt[0].p.bie_threshold != p.bie_threshold)
+		return 3;
+	double G[6][6], U[6][6], lam[6];
+	{
+		double JT0[N][6];
+#pragma unroll
+		for (int j = 0; j < N; j++)
+#pragma unroll
+			for (int a = 0; a < 6; a++) JT0[j][a] = S[(int64_t)(BL::JT0 + j * 6 + a) * cap];
+#pragma unroll
+		for (int a = 0; a < 6; a++)
+#pragma unroll
+			for (int b = 0; b <= a; b++) {
+				double s = 0.0;
+#pragma unroll
+				for (int j = 0; j < N; j++) s += JT0[j][a] * JT0[j][b];
+				G[a][b] = s;
+				G[b][a] = s;
+			}
+	}
+	int k1 = 0, k2 = 0;
+#pragma unroll
+	for (int r = 0; r < N; r++) {
+		const double m = S[(int64_t)(BL::MDIAG + r) * cap];
+		k1 += (p.bie_threshold - m > 0.0) ? 1 : 0;
+		if (HAS_JT) k2 += (P.jt[0].p.bie_threshold - m > 0.0) ? 1 : 0;
+	}
+	sym_eig6(G, U, lam);
+#pragma unroll
+	for (int a = 0; a < 5; a++)
+#pragma unroll
+		for (int b = a + 1; b < 6; b++) {
+			if (lam[b] > lam[a]) {
+				const double tl = lam[a];
+				lam[a] = lam[b];
+				lam[b] = tl;
+#pragma unroll
+				for (int k = 0; k < 6; k++) {
+					const double tu = U[k][a];
+					U[k][a] = U[k][b];
+					U[k][b] = tu;
+				}
+			}
+		}
+	double sig[6];
+#pragma unroll
+	for (int a = 0; a < 6; a++) sig[a] = sqrt(fmax(lam[a], 0.0));
+	if (sig[0] < p.s_abs_tol) return 3;	 // fully singular task
+	int n_ns = 6;
+	double alpha = 1.0;
+#pragma unroll
+	for (int c = 5; c >= 1; c--) {
+		const double icn = sig[c] / sig[0];
+		if (icn < p.s_max) {
+			n_ns = c;
+			alpha = fmin(fmax((icn - p.s_min) / (p.s_max - p.s_min), 0.0), 1.0);
+		}
+	}
+	const int n_s = 6 - n_ns;
+	if (n_s > 2) return 3;
+	if (p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES && k1 >= 2) return 3;
+	if (HAS_JT && P.jt[0].p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES && k2 >= 2) return 3;
+	if (n_s > 0 && !p.singularity_handling_enabled) return 3;
+#pragma unroll
+	for (int a = 0; a < 6; a++) {
+		S[(int64_t)(BL::SIG + a) * cap] = sig[a];
+#pragma unroll
+		for (int b = 0; b < 6; b++) S[(int64_t)(BL::U + a * 6 + b) * cap] = U[a][b];
+	}
+	S[(int64_t)BL::ALPHA * cap] = alpha;
+	return n_s;
+}
+
+// The state parked by the fused kernel and the classification kernel, then blend_path of the variant.
+template <int N, int NS, bool HAS_JT, bool MOTION>
+DEVI void blend_variant(const OscProgram& P, const int64_t i, const int64_t slot) {
+	using BL = BlendLayout<N>;
+	const int64_t cap = P.blend_cap;
+	const BlendScratchSource<N> src{P.blend_scratch + slot, cap};
+	double q[N], dq[N], sig[6], x[3], Rc[9];
+#pragma unroll
+	for (int r = 0; r < N; r++) {
+		q[r] = src.at(BL::Q + r);
+		dq[r] = src.at(BL::DQ + r);
+	}
+#pragma unroll
+	for (int a = 0; a < 6; a++) sig[a] = src.at(BL::SIG + a);
+#pragma unroll
+	for (int k = 0; k < 3; k++) x[k] = src.at(BL::X + k);
+#pragma unroll
+	for (int k = 0; k < 9; k++) Rc[k] = src.at(BL::RC + k);
+	const double alpha = src.at(BL::ALPHA);
+	if (!blend_path<N, NS, HAS_JT, BlendScratchSource<N>, MOTION>(P, i, q, dq, src, sig, alpha, x, Rc, OSC_STATUS_SINGULAR_PATH)) {
+		// cannot happen: blend_classify sends every case blend_path refuses to the general path before any state is touched
+		const int64_t NR = P.n_robots;
+#pragma unroll
+		for (int j = 0; j < N; j++) P.tau[(int64_t)j * NR + i] = __longlong_as_double(0x7ff8000000000000LL);
+		P.status[i] = OSC_STATUS_SINGULAR_PATH | OSC_STATUS_UNHANDLED;
+	}
+}
+
+template <int N, bool HAS_JT>
+__global__ void __launch_bounds__(64) osc_blend_classify_kernel(const __grid_constant__ OscProgram P) {
+	asm volatile("griddepcontrol.launch_dependents;");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	// the variant lists were cleared by the last general-path kernel of the previous cycle
+	if (P.general_done) {
+		if ((threadIdx.x & 31) == 0)
+			while ((int32_t)(ld_acquire_u32(P.general_done) - (P.epoch - 1u)) < 0) __nanosleep(128);
+		__syncwarp();
+	}
+	const int32_t count = P.sing_count[P.sing_parity];
+	const int stride = gridDim.x * blockDim.x;
+	const int lane = threadIdx.x & 31;
+	for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count; base += stride) {
+		const int slot = base + lane;
+		int variant = -1;
+		int32_t robot = 0;
+		if (slot < count) {
+			robot = P.sing_list[slot];
+			variant = blend_classify<N, HAS_JT>(P, (int64_t)slot);
+		}
+#pragma unroll
+		for (int v = 0; v < 4; v++) {
+			const unsigned m = __ballot_sync(0xffffffffu, variant == v);
+			if (m) {
+				const int leader = __ffs(m) - 1;
+				int32_t at = 0;
+				if (lane == leader) at = atomicAdd(&P.blend_counts[v], __popc(m));
+				at = __shfl_sync(0xffffffffu, at, leader);
+				if (variant == v) P.blend_lists[(int64_t)v * P.blend_cap + at + __popc(m & ((1u << lane) - 1u))] = (v == 3) ? robot : slot;
+			}
+		}
+	}
+}
+
+// The three variant lists are cut into chunks of one block each and the chunks of all three dealt to the blocks together:
+// a block (hence a warp) only ever executes one variant at a time, and the three lists are worked on at the same time.
+template <int N, int NS, bool HAS_JT, bool MOTION>
+DEVI void blend_variant_chunk(const OscProgram& P, int chunk, int32_t count) {
+	const int k = chunk * (int)blockDim.x + (int)threadIdx.x;
+	if (k < count) {
+		const int32_t slot = P.blend_lists[(int64_t)NS * P.blend_cap + k];
+		blend_variant<N, NS, HAS_JT, MOTION>(P, (int64_t)P.sing_list[slot], (int64_t)slot);
+	}
+}
+template <int N, bool HAS_JT, bool MOTION, int MINB = 4>
+__global__ void __launch_bounds__(64, MINB) osc_blend_variants_kernel(const __grid_constant__ OscProgram P) {
+	asm volatile("griddepcontrol.launch_dependents;");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	const int32_t c0 = P.blend_counts[0], c1 = P.blend_counts[1], c2 = P.blend_counts[2];
+	const int bs = (int)blockDim.x;
+	const int b1 = (c1 + bs - 1) / bs, b2 = (c2 + bs - 1) / bs, b0 = (c0 + bs - 1) / bs;
+	// longest chunks first (two singular directions), so that the short ones fill the tail
+	for (int w = blockIdx.x; w < b1 + b2 + b0; w += gridDim.x) {
+		if (w < b2)
+			blend_variant_chunk<N, 2, HAS_JT, MOTION>(P, w, c2);
+		else if (w < b2 + b1)
+			blend_variant_chunk<N, 1, HAS_JT, MOTION>(P, w - b2, c1);
+		else
+			blend_variant_chunk<N, 0, HAS_JT, MOTION>(P, w - b2 - b1, c0);
+	}
+}
+
+template <int N>
+__global__ void __launch_bounds__(64, OSC_GENERIC_MIN_BLOCKS) osc_blend_fallback_kernel(const __grid_constant__ OscProgram P) {
+	asm volatile("griddepcontrol.launch_dependents;");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	const int32_t count = P.blend_counts[3];
+	const int32_t* list = P.blend_lists + (int64_t)3 * P.blend_cap;
+	const int stride = gridDim.x * blockDim.x;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) generic_cycle_one<N>(P, (int64_t)list[k], OSC_STATUS_SINGULAR_PATH);
+	publish_general_done(P, P.sing_count[P.sing_parity], P.blend_counts);
 }
 
 }  // namespace osc

@@ -55,6 +55,8 @@ struct osc_handle {
 	size_t scratch_doubles = 0;
 	int32_t* h_seen = nullptr;	// mapped pinned: hand-over count of the last completed cycle
 	int clean_cycles = 0;
+	int blend_split = -1;  // split blending path: -1 not decided, 0 off (SAI_B200_BLEND_SPLIT=0 or no memory), 1 allocate when needed, 2 allocated
+	int64_t blend_split_min = 0;  // hand-over count (host hint) from which the split path is used
 	std::vector<void*> allocations;
 	std::string err;
 	int64_t launches = 0;
@@ -1135,6 +1137,16 @@ int osc_enable_joint_limit_avoidance(osc_handle* h, int enabled) {
 	return OSC_OK;
 }
 
+int osc_debug_general_path_counts(osc_handle* h, int32_t* out4) {
+	ENTER(h);
+	if (!out4) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null output");
+	for (int k = 0; k < 4; k++) out4[k] = -1;
+	if (!h->prog.blend_counts) return OSC_OK;  // the split blending path has not been used by this handle
+	CUDA_TRY(h, cudaMemcpyAsync(out4, h->prog.blend_counts + 4, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+	CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+	return OSC_OK;
+}
+
 int osc_debug_block_times(osc_handle* h, int enabled, unsigned long long* out, int64_t out_capacity) {
 	ENTER(h);
 	const size_t blocks = ((size_t)h->NR + osc::kCycleBlock - 1) / osc::kCycleBlock;
@@ -1190,6 +1202,38 @@ static int run_cycle(osc_handle* h, double* tau_out, int mem_kind, bool sync_hos
 		const int32_t seen = *(volatile int32_t*)h->h_seen;
 		h->clean_cycles = (seen == 0) ? h->clean_cycles + 1 : 0;
 		h->prog.general_grid_small = h->clean_cycles >= 4 ? 1 : 0;
+		// Flagship hierarchy with MANY robots on the general path (more than the single blending kernel holds in a wave and
+		// a half): run it as the three kernels of the split blending path (osc_blend.cuh), which keep their speed beyond one
+		// wave.  The scratch block (1.6 KB per robot for seven joints) is allocated the first time that happens.
+		// SAI_B200_BLEND_SPLIT=0: never (osc_blend_kernel alone);  =1: always, from the first cycle on (tests).
+		if (h->blend_split == -1) {
+			const char* e = getenv("SAI_B200_BLEND_SPLIT");
+			h->blend_split = (h->sig_R == 6 && h->prog.mft[0].full) ? ((e && e[0] == '0') ? 0 : 1) : 0;
+			h->blend_split_min = (e && e[0] == '1') ? 0 : 49152;
+		}
+		const bool many = h->blend_split > 0 && (int64_t)seen >= h->blend_split_min && (seen > 0 || h->blend_split_min == 0);
+		if (many && h->blend_split == 1) {
+			const size_t cap = (size_t)h->NR, doubles = (size_t)blend_scratch_doubles(h->model.n);
+			void *a = nullptr, *b = nullptr, *c = nullptr;
+			if (cudaMalloc(&a, cap * doubles * sizeof(double)) == cudaSuccess && cudaMalloc(&b, cap * 4 * sizeof(int32_t)) == cudaSuccess &&
+				cudaMalloc(&c, 8 * sizeof(int32_t)) == cudaSuccess && cudaMemsetAsync(c, 0, 8 * sizeof(int32_t), h->stream) == cudaSuccess) {
+				h->allocations.push_back(a);
+				h->allocations.push_back(b);
+				h->allocations.push_back(c);
+				h->prog.blend_scratch = (double*)a;
+				h->prog.blend_lists = (int32_t*)b;
+				h->prog.blend_counts = (int32_t*)c;
+				h->prog.blend_cap = (int64_t)cap;
+				h->blend_split = 2;
+			} else {  // no room: stay with the single kernel
+				cudaGetLastError();
+				if (a) cudaFree(a);
+				if (b) cudaFree(b);
+				if (c) cudaFree(c);
+				h->blend_split = 0;
+			}
+		}
+		h->prog.blend_split_on = (many && h->blend_split == 2) ? 1 : 0;
 	}
 	cudaError_t e;
 	if (h->otg_tasks > 0) {	 // the tasks' internal OTG produces this cycle's desired state first (JointTask.cpp:313-319, MotionForceTask.cpp:394-407)
@@ -1209,7 +1253,8 @@ static int run_cycle(osc_handle* h, double* tau_out, int mem_kind, bool sync_hos
 	}
 	if (e == cudaErrorNotSupported) return fail(h, OSC_ERR_UNSUPPORTED, "no kernel compiled for this hierarchy signature");
 	CUDA_TRY(h, e);
-	h->launches += (h->sig_R > 0) ? 2 : 1;  // fused cycle kernel (+ the SVD-path kernel when a motion-force task leads)
+	// fused cycle kernel (+ the general-path kernel when a motion-force task leads, or the three of the split blending path)
+	h->launches += (h->sig_R > 0) ? (osc::blend_split_selected(h->prog) ? 4 : 2) : 1;
 	h->prog.sing_parity ^= 1;
 	if (mem_kind == OSC_MEM_HOST) {
 		CUDA_TRY(h, cudaMemcpyAsync(tau_out, h->d_tau, (size_t)h->model.n * h->NR * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -173,6 +173,35 @@ DEVI void prefetch_block_rows(const OscProgram& P, uint64_t blk) {
 	}
 }
 
+// Hand-over to the split blending path: the scratch block of list slot `slot` (BlendLayout, osc_blend.cuh) receives the
+// state, the pose of the control frame, gravity, the factor of M and the Jacobian columns staged in shared memory (their Gram
+// matrix did not survive the non-singularity test: the classification kernel forms it again).  Only lanes that hand a robot
+// over get here.
+template <int N>
+DEVI void park_for_blend(const OscProgram& P, int slot, int64_t i, const double (&q)[N], const double x[3], const double Rc[9], const double (&Mdiag)[N],
+						 const double (&grav)[N], const SmTri<N, kCycleBlock>& Ls, const double* Js) {
+	using BL = BlendLayout<N>;
+	const int64_t cap = P.blend_cap, NR = P.n_robots;
+	double* S = P.blend_scratch + slot;
+	constexpr int sms = kCycleBlock;
+#pragma unroll
+	for (int j = 0; j < N; j++) {
+		S[(int64_t)(BL::Q + j) * cap] = q[j];
+		S[(int64_t)(BL::DQ + j) * cap] = P.dq[(int64_t)j * NR + i];
+		S[(int64_t)(BL::MDIAG + j) * cap] = Mdiag[j];
+		S[(int64_t)(BL::GRAV + j) * cap] = grav[j];
+		S[(int64_t)(BL::INVD + j) * cap] = Ls.invd(j);
+#pragma unroll
+		for (int c = 0; c <= j; c++) S[(int64_t)(BL::LL + j * (j + 1) / 2 + c) * cap] = Ls.L(j, c);
+#pragma unroll
+		for (int a = 0; a < 6; a++) S[(int64_t)(BL::JT0 + j * 6 + a) * cap] = Js[(size_t)(j * 6 + a) * sms];
+	}
+#pragma unroll
+	for (int k = 0; k < 3; k++) S[(int64_t)(BL::X + k) * cap] = x[k];
+#pragma unroll
+	for (int k = 0; k < 9; k++) S[(int64_t)(BL::RC + k) * cap] = Rc[k];
+}
+
 // Signature <N, R, HAS_JT, FULL>:  R = rank of a leading MotionForceTask (0: none), FULL = that task controls all six
 // directions (B = I), HAS_JT = a full JointTask closes the hierarchy.
 // Dynamic shared memory: cycle_smem_doubles<N, R>() doubles per thread,
@@ -417,13 +446,31 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				const int leader = __ffs(m) - 1;
 				int base = 0;
 				if (lane == leader) {
-					// the list of this parity was last read by the general-path kernel two cycles ago
-					if (P.general_done)
-						while ((int32_t)(ld_acquire_u32(P.general_done) - (P.epoch - 2u)) < 0) __nanosleep(256);
+					// the list of this parity was last read by the general-path kernel two cycles ago; the scratch block of the split
+					// blending path is not double-buffered: the previous cycle's general path must be through with it
+					if (P.general_done) {
+						const uint32_t need = P.epoch - ((R == 6 && FULL && P.blend_split_on) ? 1u : 2u);
+						while ((int32_t)(ld_acquire_u32(P.general_done) - need) < 0) __nanosleep(256);
+					}
 					base = atomicAdd(&P.sing_count[P.sing_parity], __popc(m));
 				}
 				base = __shfl_sync(m, base, leader);
-				P.sing_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+				const int slot = base + __popc(m & ((1u << lane) - 1u));
+				P.sing_list[slot] = (int32_t)i;
+				if constexpr (R == 6 && FULL) {
+					// split blending path (osc_blend.cuh): leave what is already known about this robot in its scratch block
+					if (P.blend_split_on) {
+						double gv[N];
+#pragma unroll
+						for (int j = 0; j < N; j++) {
+							if constexpr (SPEC)
+								gv[j] = gvec_out[j];
+							else
+								gv[j] = P.gravity_comp ? smt[(size_t)(kSmFactor<N> + N * R + j) * sms] : 0.0;
+						}
+						park_for_blend<N>(P, slot, (int64_t)i, q, x, Rc, Mdiag, gv, Ls, Js);
+					}
+				}
 				alive = false;	// the general-path kernel owns this robot from here on
 				handed_over = true;
 			}

@@ -189,6 +189,47 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 		cfg.numAttrs = 1;
 		if constexpr (R == 6) {
 			// flagship hierarchy: unrolled blending path (osc_blend.cuh), general path only as its fallback
+			if (P.mft[0].full && blend_split_selected(P)) {
+				// hand-overs are expected (host hint): prefix / variants / fallback as three kernels, each grid-stride over
+				// its list with as many blocks as the device holds at once
+				const osc_mft_params& mp = P.mft[0].p;
+				const bool motion = mp.force_space_dimension == 0 && mp.moment_space_dimension == 0 && !mp.closed_loop_force_control &&
+									!mp.closed_loop_moment_control && !mp.use_velocity_saturation;
+				static std::atomic<int> per_sm[64][3];
+				int dev = 0;
+				cudaGetDevice(&dev);
+				int occ[3] = {0, 0, 0};
+				for (int k = 0; k < 3; k++) {
+					occ[k] = (dev >= 0 && dev < 64) ? per_sm[dev][k].load(std::memory_order_acquire) : 0;
+					if (occ[k] == 0) {
+						cudaError_t e = k == 0	 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[k], osc_blend_classify_kernel<N, JT>, 64, 0)
+										: k == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[k], osc_blend_variants_kernel<N, JT, false>, 64, 0)
+												 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[k], osc_blend_variants_kernel<N, JT, true>, 64, 0);
+						if (e != cudaSuccess) return e;
+						if (occ[k] < 1) occ[k] = 1;
+						if (dev >= 0 && dev < 64) per_sm[dev][k].store(occ[k], std::memory_order_release);
+					}
+				}
+				const unsigned fallback_grid = cfg.gridDim.x;
+				long long g = (long long)sm_count() * occ[0];
+				cfg.gridDim = dim3((unsigned)(want < g ? want : g));
+				cudaError_t e = cudaLaunchKernelEx(&cfg, osc_blend_classify_kernel<N, JT>, P);
+				if (e != cudaSuccess) return e;
+				g = (long long)sm_count() * occ[motion ? 2 : 1];
+				cfg.gridDim = dim3((unsigned)(want < g ? want : g));
+				static const int minb_env = [] { const char* e = getenv("SAI_B200_VARIANTS_MINB"); return e ? atoi(e) : 4; }();
+				if (motion && minb_env == 6) {
+					cfg.gridDim = dim3((unsigned)(want < (long long)sm_count() * 6 ? want : (long long)sm_count() * 6));
+					e = cudaLaunchKernelEx(&cfg, osc_blend_variants_kernel<N, JT, true, 6>, P);
+				} else if (motion && minb_env == 8) {
+					cfg.gridDim = dim3((unsigned)(want < (long long)sm_count() * 8 ? want : (long long)sm_count() * 8));
+					e = cudaLaunchKernelEx(&cfg, osc_blend_variants_kernel<N, JT, true, 8>, P);
+				} else
+				e = motion ? cudaLaunchKernelEx(&cfg, osc_blend_variants_kernel<N, JT, true>, P) : cudaLaunchKernelEx(&cfg, osc_blend_variants_kernel<N, JT, false>, P);
+				if (e != cudaSuccess) return e;
+				cfg.gridDim = dim3(fallback_grid);
+				return cudaLaunchKernelEx(&cfg, osc_blend_fallback_kernel<N>, P);
+			}
 			if (P.mft[0].full) return cudaLaunchKernelEx(&cfg, osc_blend_kernel<N, JT>, P);
 		}
 		return cudaLaunchKernelEx(&cfg, osc_singular_kernel<N>, P);

@@ -123,6 +123,18 @@ struct DevTask {
 	int32_t index; // index into mft[] / jt[]
 };
 
+// scratch block of the split blending path (osc_blend.cuh): doubles per list slot, and where each quantity sits
+constexpr int blend_scratch_doubles(int n) { return 11 * n + n * (n + 1) / 2 + 55; }
+template <int N>
+struct BlendLayout {
+	// written by the fused kernel when it hands the robot over (park_for_blend, osc_cycle.cuh): state, pose, gravity, M = L L^T
+	// and the Jacobian (transposed);  written by the classification kernel: U, SIG, ALPHA
+	static constexpr int Q = 0, DQ = Q + N, LL = DQ + N, INVD = LL + N * (N + 1) / 2, MDIAG = INVD + N, JT0 = MDIAG + N, U = JT0 + 6 * N,
+						 SIG = U + 36, ALPHA = SIG + 6, X = ALPHA + 1, RC = X + 3, GRAV = RC + 9, COUNT = GRAV + N;
+};
+static_assert(BlendLayout<OSC_MAX_DOF>::COUNT == blend_scratch_doubles(OSC_MAX_DOF) && BlendLayout<4>::COUNT == blend_scratch_doubles(4),
+			  "blend_scratch_doubles out of step with BlendLayout");
+
 struct OscProgram {
 	DevModel model;
 	int32_t n_tasks;
@@ -152,4 +164,10 @@ struct OscProgram {
 	uint32_t epoch;			 // cycle number of this launch (31 bits used)
 	unsigned long long* block_times;  // measurement aid (osc_debug_block_times): globaltimer at block start / end, 8 cycles deep; normally null
 	int32_t general_grid_small;	 // host hint: the last cycles handed nothing over, a handful of general-path blocks is enough
+	// split blending path (osc_blend.cuh): scratch block, variant lists [4][blend_cap] and their counters; null until needed
+	double* blend_scratch;	// blend_scratch_doubles(n) x blend_cap
+	int32_t* blend_lists;
+	int32_t* blend_counts;	// [0..3] list counters, [4] block completion counter
+	int64_t blend_cap;
+	int32_t blend_split_on;	 // host decision for this cycle (the hint says many robots are on the general path)
 };

@@ -23,6 +23,12 @@ constexpr int kCycleBlock = OSC_CYCLE_BLOCK;
 // cudaErrorNotSupported when the dof is not compiled in (OSC_CYCLE_DOFS).
 cudaError_t launch_cycle(int n, int R, bool has_jt, const OscProgram& P, cudaStream_t stream);
 bool cycle_signature_available(int n, int R, bool has_jt);
+// the general path of this launch runs as the three kernels of the split blending path (osc_blend.cuh) instead of osc_blend_kernel:
+// flagship hierarchy, pipelined handle, and the host hint says that many robots are on the general path (osc_capi.cu, run_cycle)
+inline bool blend_split_selected(const OscProgram& P) {
+	return P.blend_split_on && P.blend_scratch != nullptr && P.general_done != nullptr && !P.general_grid_small && P.n_tasks >= 1 && P.tasks[0].type == OSC_TASK_MOTION_FORCE &&
+		   P.mft[0].full && P.mft[0].rank == 6;
+}
 
 cudaError_t launch_popc_probe(const OscProgram& P, int mft_index, int K, const double* fd, const double* fs, const double* vcl, const double* vr,
 							  double kv, double kff, double* out, cudaStream_t stream);

@@ -59,7 +59,8 @@ DEVI void publish_cycle(const OscProgram& P, bool handed_over) {
 // end of a general-path kernel: the last block to finish clears the list counter it consumed and publishes the cycle number.
 // The hint for the host (a mapped host word) is only rewritten when the count changes: the kernel cannot retire before a
 // write that crosses PCIe has been acknowledged, which costs microseconds of single-cycle latency.
-DEVI void publish_general_done(const OscProgram& P, int32_t count) {
+DEVI void publish_general_done(const OscProgram& P, int32_t count, int32_t* variant_counts = nullptr) {
+	// variant_counts (split blending path, osc_blend.cuh, pipelined handles only): the four list counters to clear ([4..7]: copy of the last cycle's)
 	if (!P.general_done) return;
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -70,6 +71,11 @@ DEVI void publish_general_done(const OscProgram& P, int32_t count) {
 			if (last) P.general_done[1] = 0u;
 		}
 		if (last) {
+			if (variant_counts)
+				for (int k = 0; k < 4; k++) {
+					variant_counts[4 + k] = variant_counts[k];	// kept for osc_debug_general_path_counts
+					variant_counts[k] = 0;
+				}
 			P.sing_count[P.sing_parity] = 0;
 			st_release_u32(P.general_done, P.epoch);
 			if (P.host_seen && (uint32_t)count != P.general_done[2]) {

@@ -676,8 +676,14 @@ def test_pipelined_back_to_back_cycles(filtered):
         assert ((out[True][3] & sp.capi.STATUS_SINGULAR_PATH) != 0).sum() == 0
     else:
         assert ((out[True][3] & sp.capi.STATUS_SINGULAR_PATH) != 0).mean() > 0.3      # most blocks handed robots over
-    for a, b in zip(out[True][:3], out[False][:3]):
-        assert np.array_equal(a, b)
+    if os.environ.get("SAI_B200_BLEND_SPLIT") == "1" and not filtered:
+        # the split blending path (forced on for the pipelined handle) starts from the fused kernel's kinematics, the single
+        # blending kernel of the other handle from its own: same results to rounding, not bit for bit
+        for a, b in zip(out[True][:3], out[False][:3]):
+            assert np.abs(a - b).max() <= 1e-9 * max(1.0, np.abs(b).max())
+    else:
+        for a, b in zip(out[True][:3], out[False][:3]):
+            assert np.array_equal(a, b)
     ob = OracleBatch("panda", 64); ob.set_state(q[:64], dq[:64])
     omft = ob.add_mft(link, (np.eye(3), np.array(pt))); ojt = ob.add_jt(); ob.finalize()
     for i in range(64):
@@ -786,3 +792,55 @@ def test_config3_full_size_262144_robots_sampled_parity():
     for i in range(NS, N, 499):            # duplicates of a sampled robot: bit-identical torques and passivity state
         j = int(pick[i])
         assert np.array_equal(tau[i], tau[j]) and np.array_equal(popc[i], popc[j])
+
+
+def test_split_blending_path_131072_robots_sampled_parity():
+    """Config 4's branch at scale: 131,072 uniformly sampled Panda states, 57 % of them inside the reference's blending band
+    (SingularityHandler.cpp:75-368).  The first cycle runs them through the single blending kernel; its hand-over count tells the
+    host that the list is longer than that kernel holds at once, and the following cycles take the split path (the fused kernel
+    parks kinematics and dynamics, classification kernel, one variant per warp, general path for the rest).  A 256-robot sample
+    against the reference's compiled control law at every cycle, duplicates bit-identical, and the distribution over the variants
+    from the debug counters: the blending kernels, not the rolled general path, must have handled the robots."""
+    import ctypes as C
+    import sai_primitives_b200 as sp
+    N, NS, K = 131072, 256, 4
+    base_q, base_dq, _ = sample_states("panda", NS)
+    rng = np.random.default_rng(21)
+    pick = rng.integers(0, NS, N); pick[:NS] = np.arange(NS)
+    link, pt = TASK_POINTS["panda"]
+    comp = (np.eye(3), np.array(pt))
+    robot = sp.BatchedRobot("panda", N)
+    robot.setQ(base_q[pick]); robot.setDq(base_dq[pick]); robot.updateModel()
+    mft = sp.MotionForceTask(robot, link, comp); jt = sp.JointTask(robot)
+    ctrl = sp.RobotController(robot, [mft, jt])
+    ob = OracleBatch("panda", NS); ob.set_state(base_q, base_dq)
+    omft = ob.add_mft(link, comp); ojt = ob.add_jt()
+    ob.finalize()
+    x0 = mft.getCurrentPosition()[:NS]; R0 = mft.getCurrentOrientation()[:NS]
+    xd = np.zeros((NS, 3)); Rd = np.zeros((NS, 3, 3)); gq = np.zeros((NS, 7))
+    for i in range(NS):
+        g = rng_for(i, stream=5)
+        xd[i] = x0[i] + g.uniform(-0.05, 0.05, 3); Rd[i] = R0[i] @ rot_exp(g.uniform(-0.2, 0.2, 3)); gq[i] = base_q[i] + g.uniform(-0.2, 0.2, 7)
+        omft[i].setGoalPosition(xd[i]); omft[i].setGoalOrientation(Rd[i]); ojt[i].setGoalPosition(gq[i])
+    mft.setGoalPosition(xd[pick]); mft.setGoalOrientation(Rd[pick]); jt.setGoalPosition(gq[pick])
+    lib = sp.capi.load_library()
+    counts = (C.c_int32 * 4)()
+    for k in range(K):
+        ctrl.updateControllerTaskModels()
+        tau = ctrl.computeControlTorques()
+        ref = ob.cycle()
+        assert rel_err(tau[:NS], ref).max() < REL_TOL, k
+        st = robot.status()
+        assert (st & sp.capi.STATUS_UNHANDLED).sum() == 0
+        assert lib.osc_debug_general_path_counts(robot.handle, counts) == 0
+        if k == 0:
+            assert list(counts) == [-1, -1, -1, -1]          # the single kernel took the first cycle
+        else:
+            c = np.array(list(counts))
+            on_general_path = int(((st & sp.capi.STATUS_SINGULAR_PATH) != 0).sum())
+            assert c[1] + c[2] > 0.4 * N and c[3] < 0.02 * N, c
+            assert on_general_path <= c.sum() <= on_general_path + c[0] + c[3]    # variant 0 / general path: may turn out non-singular
+        qk = base_q + 0.002 * (k + 1) * base_dq
+        robot.setQ(qk[pick]); robot.updateModel(); ob.set_state(qk, base_dq)
+    for i in range(NS, N, 997):
+        assert np.array_equal(tau[i], tau[int(pick[i])])
