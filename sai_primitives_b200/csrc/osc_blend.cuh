@@ -20,13 +20,14 @@
 #include "osc_tasks.cuh"
 #define OSC_EIG6_LEAN_MATH
 #include "osc_eig6.h"
+#include <type_traits>
 
 namespace osc {
 
 // (A - delta z z^T / kappa)^-1 y for A = Rb^T Rb given by its upper-triangular factor stored in T[C0 + i][C0 + j] (i <= j),
 // size S; rinv = reciprocal diagonal.  use_sm = false gives plain A^-1 y.
-template <int N, int S, int C0>
-DEVI void solve_block_sm(const double (&T)[N][6], const double (&rinv)[6], double (&y)[S], const double (&z)[S], bool use_sm, double delta,
+template <int N, int S, int C0, class TT>
+DEVI void solve_block_sm(const TT& T, const double (&rinv)[6], double (&y)[S], const double (&z)[S], bool use_sm, double delta,
 						 double kappa) {
 	auto solve = [&](double(&x)[S]) {
 #pragma unroll
@@ -97,9 +98,16 @@ struct BlendScratchSource {
 // Everything after the eigen-decomposition, for NS singular directions (NS = 0: the thin band of non-singular robots
 // the sound test of the fast kernel rejects).  Returns false when the case must go to the general path.
 // MOTION: the task is under pure motion control (host check, as for the fused kernel): only the two PID laws are compiled in and F = 0.
-template <int N, int NS, bool HAS_JT, class Src, bool MOTION = false>
+// SMEM: the factor L and the matrix T (70 of the doubles with the longest lives) are kept in shared memory, element e of
+// this thread at smem[e * kBlendBlock], instead of registers (where, with everything else, they spill).
+constexpr int kBlendBlock = 64;
+template <int N>
+constexpr int blend_smem_doubles() {
+	return N * (N + 1) / 2 + 6 * N;
+}
+template <int N, int NS, bool HAS_JT, class Src, bool MOTION = false, bool SMEM = false>
 DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const double (&dq)[N], const Src& src, const double (&sig)[6], double alpha,
-					 const double x[3], const double Rc[9], uint32_t status) {
+					 const double x[3], const double Rc[9], uint32_t status, double* smem = nullptr) {
 	constexpr int NNS = 6 - NS;
 	const int64_t NR = P.n_robots;
 	const DevModel& mdl = P.model;
@@ -241,12 +249,18 @@ DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const
 	mft_control_law<MOTION>(t, NR, i, x, Rc, v, w, P.write_observers != 0, fstar, F, status);
 
 	// dynamics factor (read only now: nothing above needs it), and the unit vector of the clamped entry through it
-	double L[N][N], invd[N], g[N], mu = 0.0;
+	typename std::conditional<SMEM, SmLowerMat<kBlendBlock>, RegMat<N, N>>::type L;
+	typename std::conditional<SMEM, SmMat<6, kBlendBlock>, RegMat<N, 6>>::type T;
+	if constexpr (SMEM) {
+		L.b = smem;
+		T.b = smem + (N * (N + 1) / 2) * kBlendBlock;
+	}
+	double invd[N], g[N], mu = 0.0;
 #pragma unroll
 	for (int r = 0; r < N; r++) {
 		invd[r] = src.invd(r);
 #pragma unroll
-		for (int c = 0; c < N; c++) L[r][c] = (c <= r) ? src.l(r, c <= r ? c : 0) : 0.0;
+		for (int c = 0; c <= r; c++) L[r][c] = src.l(r, c);
 	}
 	if (sm) {
 #pragma unroll
@@ -257,7 +271,7 @@ DEVI bool blend_path(const OscProgram& P, int64_t i, const double (&q)[N], const
 	}
 	const double kappa = 1.0 + delta * mu;
 	// ---- T = X U with X = L^-1 J^T (its Householder QR follows), and the coordinates of f*, F in the rotated task basis
-	double T[N][6], au[6], bu[6];
+	double au[6], bu[6];
 	{
 		double Ue[6][6];
 #pragma unroll
@@ -846,7 +860,7 @@ DEVI int blend_classify(const OscProgram& P, const int64_t slot) {
 
 // The state parked by the fused kernel and the classification kernel, then blend_path of the variant.
 template <int N, int NS, bool HAS_JT, bool MOTION>
-DEVI void blend_variant(const OscProgram& P, const int64_t i, const int64_t slot) {
+DEVI void blend_variant(const OscProgram& P, const int64_t i, const int64_t slot, double* sm) {
 	using BL = BlendLayout<N>;
 	const int64_t cap = P.blend_cap;
 	const BlendScratchSource<N> src{P.blend_scratch + slot, cap};
@@ -863,7 +877,7 @@ DEVI void blend_variant(const OscProgram& P, const int64_t i, const int64_t slot
 #pragma unroll
 	for (int k = 0; k < 9; k++) Rc[k] = src.at(BL::RC + k);
 	const double alpha = src.at(BL::ALPHA);
-	if (!blend_path<N, NS, HAS_JT, BlendScratchSource<N>, MOTION>(P, i, q, dq, src, sig, alpha, x, Rc, OSC_STATUS_SINGULAR_PATH)) {
+	if (!blend_path<N, NS, HAS_JT, BlendScratchSource<N>, MOTION, true>(P, i, q, dq, src, sig, alpha, x, Rc, OSC_STATUS_SINGULAR_PATH, sm)) {
 		// cannot happen: blend_classify sends every case blend_path refuses to the general path before any state is touched
 		const int64_t NR = P.n_robots;
 #pragma unroll
@@ -910,28 +924,33 @@ __global__ void __launch_bounds__(64) osc_blend_classify_kernel(const __grid_con
 // The three variant lists are cut into chunks of one block each and the chunks of all three dealt to the blocks together:
 // a block (hence a warp) only ever executes one variant at a time, and the three lists are worked on at the same time.
 template <int N, int NS, bool HAS_JT, bool MOTION>
-DEVI void blend_variant_chunk(const OscProgram& P, int chunk, int32_t count) {
+DEVI void blend_variant_chunk(const OscProgram& P, int chunk, int32_t count, double* sm) {
 	const int k = chunk * (int)blockDim.x + (int)threadIdx.x;
 	if (k < count) {
 		const int32_t slot = P.blend_lists[(int64_t)NS * P.blend_cap + k];
-		blend_variant<N, NS, HAS_JT, MOTION>(P, (int64_t)P.sing_list[slot], (int64_t)slot);
+		blend_variant<N, NS, HAS_JT, MOTION>(P, (int64_t)P.sing_list[slot], (int64_t)slot, sm);
 	}
 }
-template <int N, bool HAS_JT, bool MOTION, int MINB = 4>
-__global__ void __launch_bounds__(64, MINB) osc_blend_variants_kernel(const __grid_constant__ OscProgram P) {
+// 255 registers, four blocks per SM: capping the registers for six or eight blocks costs 14 % / 21 % (profiles/r02_summary.md)
+template <int N, bool HAS_JT, bool MOTION>
+__global__ void __launch_bounds__(kBlendBlock) osc_blend_variants_kernel(const __grid_constant__ OscProgram P) {
 	asm volatile("griddepcontrol.launch_dependents;");
 	asm volatile("griddepcontrol.wait;" ::: "memory");
+	extern __shared__ double blend_sm[];  // blend_smem_doubles<N>() per thread
+	double* sm = blend_sm + threadIdx.x;
 	const int32_t c0 = P.blend_counts[0], c1 = P.blend_counts[1], c2 = P.blend_counts[2];
 	const int bs = (int)blockDim.x;
 	const int b1 = (c1 + bs - 1) / bs, b2 = (c2 + bs - 1) / bs, b0 = (c0 + bs - 1) / bs;
-	// longest chunks first (two singular directions), so that the short ones fill the tail
+	// Chunk w of the concatenated lists goes to block w mod gridDim.x, the most common variant (one singular direction) first: at
+	// any time nearly all blocks of an SM execute the same variant, which is what keeps its 140 KB instruction stream
+	// cached.  Longest-first and work-queue orders were measured: both lose 5-15 % beyond one wave (profiles/r02_summary.md).
 	for (int w = blockIdx.x; w < b1 + b2 + b0; w += gridDim.x) {
-		if (w < b2)
-			blend_variant_chunk<N, 2, HAS_JT, MOTION>(P, w, c2);
-		else if (w < b2 + b1)
-			blend_variant_chunk<N, 1, HAS_JT, MOTION>(P, w - b2, c1);
+		if (w < b1)
+			blend_variant_chunk<N, 1, HAS_JT, MOTION>(P, w, c1, sm);
+		else if (w < b1 + b2)
+			blend_variant_chunk<N, 2, HAS_JT, MOTION>(P, w - b1, c2, sm);
 		else
-			blend_variant_chunk<N, 0, HAS_JT, MOTION>(P, w - b2 - b1, c0);
+			blend_variant_chunk<N, 0, HAS_JT, MOTION>(P, w - b1 - b2, c0, sm);
 	}
 }
 

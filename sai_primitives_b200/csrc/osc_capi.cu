@@ -1204,7 +1204,7 @@ static int run_cycle(osc_handle* h, double* tau_out, int mem_kind, bool sync_hos
 		h->prog.general_grid_small = h->clean_cycles >= 4 ? 1 : 0;
 		// Flagship hierarchy with MANY robots on the general path (more than the single blending kernel holds in a wave and
 		// a half): run it as the three kernels of the split blending path (osc_blend.cuh), which keep their speed beyond one
-		// wave.  The scratch block (1.6 KB per robot for seven joints) is allocated the first time that happens.
+		// wave.  The scratch block (1.3 KB per robot for seven joints) is allocated the first time that happens.
 		// SAI_B200_BLEND_SPLIT=0: never (osc_blend_kernel alone);  =1: always, from the first cycle on (tests).
 		if (h->blend_split == -1) {
 			const char* e = getenv("SAI_B200_BLEND_SPLIT");

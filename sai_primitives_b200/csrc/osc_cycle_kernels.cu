@@ -195,6 +195,8 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 				const osc_mft_params& mp = P.mft[0].p;
 				const bool motion = mp.force_space_dimension == 0 && mp.moment_space_dimension == 0 && !mp.closed_loop_force_control &&
 									!mp.closed_loop_moment_control && !mp.use_velocity_saturation;
+				constexpr int vsmem = blend_smem_doubles<N>() * kBlendBlock * (int)sizeof(double);
+				static_assert(vsmem <= 48 * 1024, "variants kernel: dynamic shared memory beyond the default limit");
 				static std::atomic<int> per_sm[64][3];
 				int dev = 0;
 				cudaGetDevice(&dev);
@@ -203,8 +205,8 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 					occ[k] = (dev >= 0 && dev < 64) ? per_sm[dev][k].load(std::memory_order_acquire) : 0;
 					if (occ[k] == 0) {
 						cudaError_t e = k == 0	 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[k], osc_blend_classify_kernel<N, JT>, 64, 0)
-										: k == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[k], osc_blend_variants_kernel<N, JT, false>, 64, 0)
-												 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[k], osc_blend_variants_kernel<N, JT, true>, 64, 0);
+										: k == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[k], osc_blend_variants_kernel<N, JT, false>, kBlendBlock, vsmem)
+												 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[k], osc_blend_variants_kernel<N, JT, true>, kBlendBlock, vsmem);
 						if (e != cudaSuccess) return e;
 						if (occ[k] < 1) occ[k] = 1;
 						if (dev >= 0 && dev < 64) per_sm[dev][k].store(occ[k], std::memory_order_release);
@@ -217,17 +219,11 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 				if (e != cudaSuccess) return e;
 				g = (long long)sm_count() * occ[motion ? 2 : 1];
 				cfg.gridDim = dim3((unsigned)(want < g ? want : g));
-				static const int minb_env = [] { const char* e = getenv("SAI_B200_VARIANTS_MINB"); return e ? atoi(e) : 4; }();
-				if (motion && minb_env == 6) {
-					cfg.gridDim = dim3((unsigned)(want < (long long)sm_count() * 6 ? want : (long long)sm_count() * 6));
-					e = cudaLaunchKernelEx(&cfg, osc_blend_variants_kernel<N, JT, true, 6>, P);
-				} else if (motion && minb_env == 8) {
-					cfg.gridDim = dim3((unsigned)(want < (long long)sm_count() * 8 ? want : (long long)sm_count() * 8));
-					e = cudaLaunchKernelEx(&cfg, osc_blend_variants_kernel<N, JT, true, 8>, P);
-				} else
+				cfg.dynamicSmemBytes = vsmem;
 				e = motion ? cudaLaunchKernelEx(&cfg, osc_blend_variants_kernel<N, JT, true>, P) : cudaLaunchKernelEx(&cfg, osc_blend_variants_kernel<N, JT, false>, P);
 				if (e != cudaSuccess) return e;
 				cfg.gridDim = dim3(fallback_grid);
+				cfg.dynamicSmemBytes = 0;
 				return cudaLaunchKernelEx(&cfg, osc_blend_fallback_kernel<N>, P);
 			}
 			if (P.mft[0].full) return cudaLaunchKernelEx(&cfg, osc_blend_kernel<N, JT>, P);

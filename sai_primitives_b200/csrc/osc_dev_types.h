@@ -167,7 +167,7 @@ struct OscProgram {
 	// split blending path (osc_blend.cuh): scratch block, variant lists [4][blend_cap] and their counters; null until needed
 	double* blend_scratch;	// blend_scratch_doubles(n) x blend_cap
 	int32_t* blend_lists;
-	int32_t* blend_counts;	// [0..3] list counters, [4] block completion counter
+	int32_t* blend_counts;	// [0..3] list counters, [4..7] those of the last cycle (osc_debug_general_path_counts)
 	int64_t blend_cap;
 	int32_t blend_split_on;	 // host decision for this cycle (the hint says many robots are on the general path)
 };

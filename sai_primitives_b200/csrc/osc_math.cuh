@@ -155,8 +155,8 @@ DEVI bool cholesky_lower(double (&A)[N][N], double (&invd)[N]) {
 }
 
 // x <- L^-1 x   (L lower triangular, N x N)
-template <int N>
-DEVI void solve_lower(const double (&L)[N][N], const double (&invd)[N], double (&x)[N]) {
+template <int N, class LT>
+DEVI void solve_lower(const LT& L, const double (&invd)[N], double (&x)[N]) {
 #pragma unroll
 	for (int i = 0; i < N; i++) {
 		double s = x[i];
@@ -166,8 +166,8 @@ DEVI void solve_lower(const double (&L)[N][N], const double (&invd)[N], double (
 	}
 }
 // x <- L^-T x
-template <int N>
-DEVI void solve_lower_t(const double (&L)[N][N], const double (&invd)[N], double (&x)[N]) {
+template <int N, class LT>
+DEVI void solve_lower_t(const LT& L, const double (&invd)[N], double (&x)[N]) {
 #pragma unroll
 	for (int i = N - 1; i >= 0; i--) {
 		double s = x[i];
@@ -177,8 +177,8 @@ DEVI void solve_lower_t(const double (&L)[N][N], const double (&invd)[N], double
 	}
 }
 // y = L x
-template <int N>
-DEVI void mul_lower(const double (&L)[N][N], const double (&x)[N], double (&y)[N]) {
+template <int N, class LT>
+DEVI void mul_lower(const LT& L, const double (&x)[N], double (&y)[N]) {
 #pragma unroll
 	for (int i = 0; i < N; i++) {
 		double s = 0.0;
@@ -188,15 +188,15 @@ DEVI void mul_lower(const double (&L)[N][N], const double (&x)[N], double (&y)[N
 	}
 }
 // x <- (L L^T)^-1 x
-template <int N>
-DEVI void solve_spd(const double (&L)[N][N], const double (&invd)[N], double (&x)[N]) {
+template <int N, class LT>
+DEVI void solve_spd(const LT& L, const double (&invd)[N], double (&x)[N]) {
 	solve_lower<N>(L, invd, x);
 	solve_lower_t<N>(L, invd, x);
 }
 
 // x <- (R^T R)^-1 x  with R upper triangular R x R stored in X[C+i][j], i <= j, rinv[i] = 1 / R[i][i]
-template <int N, int R, int C>
-DEVI void solve_rtr(const double (&X)[N][R], const double (&rinv)[R], double (&x)[R]) {
+template <int N, int R, int C, class XT>
+DEVI void solve_rtr(const XT& X, const double (&rinv)[R], double (&x)[R]) {
 #pragma unroll
 	for (int i = 0; i < R; i++) {  // R^T z = x (forward)
 		double s = x[i];
@@ -216,8 +216,8 @@ DEVI void solve_rtr(const double (&X)[N][R], const double (&rinv)[R], double (&x
 // Householder QR of rows C..N-1 of X (N x R), in place:
 //   on exit X[C+i][j] (i <= j) holds R; reflector j is v_j with v_j[C+j] = vhead[j] and
 //   v_j[C+j+1..N-1] stored in X below the diagonal; H_j = I - beta[j] v_j v_j^T;  rinv[j] = 1 / R[j][j].
-template <int N, int R, int C>
-DEVI void householder_qr(double (&X)[N][R], double (&vhead)[R], double (&beta)[R], double (&rinv)[R]) {
+template <int N, int R, int C, class XT>
+DEVI void householder_qr(XT& X, double (&vhead)[R], double (&beta)[R], double (&rinv)[R]) {
 #pragma unroll
 	for (int j = 0; j < R; j++) {
 		constexpr int dummy = 0;
@@ -253,8 +253,8 @@ DEVI void householder_qr(double (&X)[N][R], double (&vhead)[R], double (&beta)[R
 }
 
 // x <- H_1 ... H_R x   (reflectors from householder_qr, acting on rows C..N-1)
-template <int N, int R, int C>
-DEVI void apply_q(const double (&X)[N][R], const double (&vhead)[R], const double (&beta)[R], double (&x)[N]) {
+template <int N, int R, int C, class XT>
+DEVI void apply_q(const XT& X, const double (&vhead)[R], const double (&beta)[R], double (&x)[N]) {
 #pragma unroll
 	for (int j = R - 1; j >= 0; j--) {
 		const int k = C + j;
@@ -268,8 +268,8 @@ DEVI void apply_q(const double (&X)[N][R], const double (&vhead)[R], const doubl
 	}
 }
 // x <- H_R ... H_1 x
-template <int N, int R, int C>
-DEVI void apply_qt(const double (&X)[N][R], const double (&vhead)[R], const double (&beta)[R], double (&x)[N]) {
+template <int N, int R, int C, class XT>
+DEVI void apply_qt(const XT& X, const double (&vhead)[R], const double (&beta)[R], double (&x)[N]) {
 #pragma unroll
 	for (int j = 0; j < R; j++) {
 		const int k = C + j;
@@ -371,6 +371,33 @@ DEVI bool sound_nonsingular_gram(double (&G)[R][R], double thr, double abs_tol) 
 	double invd[R];
 	return cholesky_lower<R>(G, invd);
 }
+
+// ---- matrices of one thread, addressed M[r][c] by the templates above, either in registers or in shared memory
+// (element e of thread t at b[e * STRIDE + t]: conflict-free, every address is base + constant after unrolling).
+template <int ROWS, int COLS>
+struct RegMat {
+	double a[ROWS][COLS];
+	DEVI double* operator[](int r) { return a[r]; }
+	DEVI const double* operator[](int r) const { return a[r]; }
+};
+template <int COLS, int STRIDE>
+struct SmMat {
+	double* b;
+	struct Row {
+		double* p;
+		DEVI double& operator[](int c) const { return p[c * STRIDE]; }
+	};
+	DEVI Row operator[](int r) const { return Row{b + r * COLS * STRIDE}; }
+};
+template <int STRIDE>
+struct SmLowerMat {	 // packed lower triangle
+	double* b;
+	struct Row {
+		double* p;
+		DEVI double& operator[](int c) const { return p[c * STRIDE]; }
+	};
+	DEVI Row operator[](int r) const { return Row{b + (r * (r + 1) / 2) * STRIDE}; }
+};
 
 // ---- lower-triangular factor staged in shared memory: element (r, c) of this thread's matrix at
 // b[(r (r + 1) / 2 + c) * STRIDE], the reciprocal diagonal behind it.  STRIDE is the (compile-time) block size, so

@@ -802,6 +802,7 @@ def test_split_blending_path_131072_robots_sampled_parity():
     against the reference's compiled control law at every cycle, duplicates bit-identical, and the distribution over the variants
     from the debug counters: the blending kernels, not the rolled general path, must have handled the robots."""
     import ctypes as C
+    import os
     import sai_primitives_b200 as sp
     N, NS, K = 131072, 256, 4
     base_q, base_dq, _ = sample_states("panda", NS)
@@ -833,7 +834,7 @@ def test_split_blending_path_131072_robots_sampled_parity():
         st = robot.status()
         assert (st & sp.capi.STATUS_UNHANDLED).sum() == 0
         assert lib.osc_debug_general_path_counts(robot.handle, counts) == 0
-        if k == 0:
+        if k == 0 and os.environ.get("SAI_B200_BLEND_SPLIT") != "1":
             assert list(counts) == [-1, -1, -1, -1]          # the single kernel took the first cycle
         else:
             c = np.array(list(counts))

@@ -4,12 +4,12 @@
 tag=${1:-r02_split}
 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/${tag}_gputest_lazy.log; tail -3 gpurun_out/${tag}_gputest_lazy.log
 SAI_B200_BLEND_SPLIT=1 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/${tag}_gputest_eager.log; tail -3 gpurun_out/${tag}_gputest_eager.log
-for mode in auto split single; do
+for mode in auto single; do
   unset SAI_B200_BLEND_SPLIT
   [ $mode = single ] && export SAI_B200_BLEND_SPLIT=0
   [ $mode = split ] && export SAI_B200_BLEND_SPLIT=1
-  for r in 65536 131072 262144 1048576; do
-    sets=8; [ $r -ge 262144 ] && sets=4; [ $r -ge 1048576 ] && sets=2
+  for r in 65536 131072 262144 1048576 4194304; do
+    sets=8; [ $r -ge 262144 ] && sets=4; [ $r -ge 1048576 ] && sets=2; [ $r -ge 4194304 ] && sets=1
     python bench.py --robots $r --sets $sets --steps 100 --warmup 10 --min-ratio 0 --no-cpu 2>/dev/null > gpurun_out/${tag}_unfiltered_${mode}_$r.json
     python -c "import json;d=json.loads(open('gpurun_out/${tag}_unfiltered_${mode}_$r.json').read().strip().splitlines()[-1]);print('$mode',$r,'%.4g cycles/s'%d['value'],'%.4f ms'%d['ms_per_step'],'launches',d.get('gpu_launches'))"
   done
