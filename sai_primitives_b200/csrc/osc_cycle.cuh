@@ -217,7 +217,9 @@ DEVI void park_for_blend(const OscProgram& P, int slot, int64_t i, const double 
 // MOTION (with SPEC only; default): the motion-force task is a full task under pure motion control, so only the two PID
 // laws are compiled in and its goals are staged through shared memory.  SPEC without MOTION keeps the general control
 // law (partial tasks, force / moment spaces, closed loops, POPC) on top of the same rolled kinematics.
-template <int N, int R, bool HAS_JT, bool FULL, bool SPEC = false, bool GRAV = false, bool MOTION = SPEC>
+// PARK (full six-dof task only): hand-overs also leave kinematics and dynamics in the scratch block of the split blending path
+// (osc_blend.cuh); a separate instantiation, because compiled into the kernel of the headline it costs 6 registers and 0.7 %.
+template <int N, int R, bool HAS_JT, bool FULL, bool SPEC = false, bool GRAV = false, bool MOTION = SPEC, bool PARK = false>
 __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(const __grid_constant__ OscProgram P) {
 	extern __shared__ double sm[];
 	// Programmatic dependent launch on both sides: the general-path kernel of this cycle may be scheduled into whatever
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 					// the list of this parity was last read by the general-path kernel two cycles ago; the scratch block of the split
 					// blending path is not double-buffered: the previous cycle's general path must be through with it
 					if (P.general_done) {
-						const uint32_t need = P.epoch - ((R == 6 && FULL && P.blend_split_on) ? 1u : 2u);
+						const uint32_t need = P.epoch - ((PARK && P.blend_split_on) ? 1u : 2u);
 						while ((int32_t)(ld_acquire_u32(P.general_done) - need) < 0) __nanosleep(256);
 					}
 					base = atomicAdd(&P.sing_count[P.sing_parity], __popc(m));
@@ -457,8 +459,9 @@ __global__ void __launch_bounds__(kCycleBlock, OSC_MIN_BLOCKS) osc_cycle_kernel(
 				base = __shfl_sync(m, base, leader);
 				const int slot = base + __popc(m & ((1u << lane) - 1u));
 				P.sing_list[slot] = (int32_t)i;
-				if constexpr (R == 6 && FULL) {
+				if constexpr (PARK) {
 					// split blending path (osc_blend.cuh): leave what is already known about this robot in its scratch block
+					static_assert(!PARK || (R == 6 && FULL), "the split blending path is for the full six-dof task");
 					if (P.blend_split_on) {
 						double gv[N];
 #pragma unroll

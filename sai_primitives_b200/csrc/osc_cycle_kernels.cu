@@ -90,7 +90,7 @@ static int sm_count() {
 	return v;
 }
 
-template <int N, int R, bool JT, bool FULL, bool SPEC = false, bool GRAV = false, bool MOTION = SPEC>
+template <int N, int R, bool JT, bool FULL, bool SPEC = false, bool GRAV = false, bool MOTION = SPEC, bool PARK = false>
 static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 	const unsigned grid = (unsigned)((P.n_robots + kCycleBlock - 1) / kCycleBlock);
 	constexpr int smem = cycle_smem_doubles<N, R, SPEC, MOTION>() * kCycleBlock * (int)sizeof(double);
@@ -100,7 +100,7 @@ static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-		cudaError_t e = cudaFuncSetAttribute(osc_cycle_kernel<N, R, JT, FULL, SPEC, GRAV, MOTION>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaError_t e = cudaFuncSetAttribute(osc_cycle_kernel<N, R, JT, FULL, SPEC, GRAV, MOTION, PARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e != cudaSuccess) return e;
 		if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
 	}
@@ -124,7 +124,7 @@ static cudaError_t launch_variant(const OscProgram& P, cudaStream_t stream) {
 		attr[0].val.programmaticStreamSerializationAllowed = 1;
 		cfg.attrs = attr;
 		cfg.numAttrs = 1;
-		cudaError_t e = cudaLaunchKernelEx(&cfg, osc_cycle_kernel<N, R, JT, FULL, SPEC, GRAV, MOTION>, P);
+		cudaError_t e = cudaLaunchKernelEx(&cfg, osc_cycle_kernel<N, R, JT, FULL, SPEC, GRAV, MOTION, PARK>, P);
 		if (e != cudaSuccess) return e;
 	}
 #if defined(OSC_TRACE)
@@ -149,14 +149,22 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 	if constexpr (R == 6) {
 		bool motion = false;
 		const bool spec = cycle_spec_eligible(P, JT, &motion);
+		// with many robots on the general path the hand-overs also park their kinematics and dynamics for the split blending path
+		const bool park = P.mft[0].full && blend_split_selected(P);
 		if (!P.mft[0].full)
 			e0 = launch_variant<N, R, JT, false>(P, stream);
-		else if (spec && motion)
+		else if (spec && motion && !park)
 			e0 = P.gravity_comp ? launch_variant<N, R, JT, true, true, true>(P, stream) : launch_variant<N, R, JT, true, true, false>(P, stream);
-		else if (spec)	// full task with force / moment control or velocity saturation
+		else if (spec && motion)
+			e0 = P.gravity_comp ? launch_variant<N, R, JT, true, true, true, true, true>(P, stream) : launch_variant<N, R, JT, true, true, false, true, true>(P, stream);
+		else if (spec && !park)	// full task with force / moment control or velocity saturation
 			e0 = P.gravity_comp ? launch_variant<N, R, JT, true, true, true, false>(P, stream) : launch_variant<N, R, JT, true, true, false, false>(P, stream);
-		else
+		else if (spec)
+			e0 = P.gravity_comp ? launch_variant<N, R, JT, true, true, true, false, true>(P, stream) : launch_variant<N, R, JT, true, true, false, false, true>(P, stream);
+		else if (!park)
 			e0 = launch_variant<N, R, JT, true>(P, stream);
+		else
+			e0 = launch_variant<N, R, JT, true, false, false, false, true>(P, stream);
 	} else if constexpr (R == 3) {
 		// the other common shape: three controlled directions (position only, or a planar task), any control law
 		bool motion = false;
