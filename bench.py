@@ -500,34 +500,43 @@ def gpu_arm(args):
     # ---- the same hierarchy on UNFILTERED states (about half of the uniformly sampled Panda states sit inside the reference's
     # singularity blending band and leave the fused kernel for the general path): reported as an extra so that the cost of
     # that path is timed by the same run, not part of `value`
-    uq, udq, _, _ = sample_batch(sp, R, local_rank, min_ratio=0.0, shard=rank + 1000)
-    urobot = sp.BatchedRobot(ROBOT, R, device=local_rank)
-    urobot.setStream(stream.cuda_stream)
-    urobot.setQ(uq); urobot.setDq(udq); urobot.updateModel()
-    umft = sp.MotionForceTask(urobot, LINK, (np.eye(3), np.array(POINT))); ujt = sp.JointTask(urobot)
-    umft.disableInternalOtg(); ujt.disableInternalOtg()
-    uctrl = sp.RobotController(urobot, [umft, ujt])
-    ug = make_goals(rng, umft.getCurrentPosition(), umft.getCurrentOrientation(), uq)
-    umft.setGoalPosition(ug["xd"]); umft.setGoalOrientation(ug["Rd"]); umft.setGoalLinearVelocity(ug["vd"]); umft.setGoalAngularVelocity(ug["wd"])
-    ujt.setGoalPosition(ug["qd"])
-    ud = dict(robot=urobot, q=torch.from_numpy(np.ascontiguousarray(uq.T)).to(dev), dq=torch.from_numpy(np.ascontiguousarray(udq.T)).to(dev),
-              tau=torch.zeros((n, R), dtype=torch.float64, device=dev))
-    torch.cuda.set_stream(stream)
-    for _ in range(3):
-        step_device(ud)
-    barrier()
-    ue0, ue1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ue0.record()
-    for _ in range(30):
-        step_device(ud)
-    ue1.record()
-    barrier()
-    unfiltered_ms = ue0.elapsed_time(ue1) / 30
-    ust = urobot.status()
-    unfiltered_singular = float(((ust & capi.STATUS_SINGULAR_PATH) != 0).mean())
-    if (ust & capi.STATUS_UNHANDLED).any():
-        raise SystemExit("bench: unfiltered batch left the CUDA path")
-    urobot.close()
+    def unfiltered_run(Ru, cycles, shard):
+        uq, udq, _, _ = sample_batch(sp, Ru, local_rank, min_ratio=0.0, shard=shard)
+        urobot = sp.BatchedRobot(ROBOT, Ru, device=local_rank)
+        urobot.setStream(stream.cuda_stream)
+        urobot.setQ(uq); urobot.setDq(udq); urobot.updateModel()
+        umft = sp.MotionForceTask(urobot, LINK, (np.eye(3), np.array(POINT))); ujt = sp.JointTask(urobot)
+        umft.disableInternalOtg(); ujt.disableInternalOtg()
+        uctrl = sp.RobotController(urobot, [umft, ujt])
+        ug = make_goals(rng, umft.getCurrentPosition(), umft.getCurrentOrientation(), uq)
+        umft.setGoalPosition(ug["xd"]); umft.setGoalOrientation(ug["Rd"]); umft.setGoalLinearVelocity(ug["vd"]); umft.setGoalAngularVelocity(ug["wd"])
+        ujt.setGoalPosition(ug["qd"])
+        ud = dict(robot=urobot, q=torch.from_numpy(np.ascontiguousarray(uq.T)).to(dev), dq=torch.from_numpy(np.ascontiguousarray(udq.T)).to(dev),
+                  tau=torch.zeros((n, Ru), dtype=torch.float64, device=dev))
+        torch.cuda.set_stream(stream)
+        for _ in range(3):
+            step_device(ud)
+            urobot.sync()     # the host reads the hand-over count of completed cycles: let it settle on the path it will use
+        barrier()
+        ue0, ue1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ue0.record()
+        for _ in range(cycles):
+            step_device(ud)
+        ue1.record()
+        barrier()
+        ms = ue0.elapsed_time(ue1) / cycles
+        ust = urobot.status()
+        share = float(((ust & capi.STATUS_SINGULAR_PATH) != 0).mean())
+        if (ust & capi.STATUS_UNHANDLED).any():
+            raise SystemExit("bench: unfiltered batch left the CUDA path")
+        del uctrl
+        urobot.close()
+        return ms, share
+
+    unfiltered_ms, unfiltered_singular = unfiltered_run(R, 30, rank + 1000)
+    # and at a batch size where the hand-over list is many waves long (the split blending path)
+    R_LARGE = 1048576
+    unfiltered_large_ms, unfiltered_large_singular = (unfiltered_run(R_LARGE, 10, rank + 2000) if R < R_LARGE else (float("nan"), float("nan")))
 
     # ---- end to end through the C ABI with pinned HOST buffers: every step copies q, dq host->device and tau
     # device->host inside the timed region.  The n_sets controller instances run on their own streams
@@ -599,9 +608,9 @@ def gpu_arm(args):
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([e2e_ms, multi_ms, link_ms, unfiltered_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_ms, multi_ms, link_ms, unfiltered_ms, unfiltered_large_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms, multi_ms, link_ms, unfiltered_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        e2e_ms, multi_ms, link_ms, unfiltered_ms, unfiltered_large_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
     value = world * R * args.steps / (total_ms * 1e-3)
     e2e_value = world * R * e2e_steps / (e2e_ms * 1e-3)
 
@@ -648,7 +657,12 @@ def gpu_arm(args):
                       "unfiltered_states": {"value": world * R / (unfiltered_ms * 1e-3), "unit": UNIT, "ms_per_step": unfiltered_ms,
                                             "robots_on_the_general_path": unfiltered_singular,
                                             "what": "same hierarchy and batch size, uniformly sampled states without the s_min/s_max filter: the "
-                                                    "robots inside the reference's blending band take the general (SVD) path; 30 cycles, CUDA events"}},
+                                                    "robots inside the reference's blending band take the general (SVD) path; 30 cycles, CUDA events"},
+                      "unfiltered_states_1m_robots": (None if not (unfiltered_large_ms == unfiltered_large_ms) else
+                                                      {"value": world * R_LARGE / (unfiltered_large_ms * 1e-3), "unit": UNIT, "ms_per_step": unfiltered_large_ms,
+                                                       "robots_per_gpu": R_LARGE, "robots_on_the_general_path": unfiltered_large_singular,
+                                                       "what": "the same at 1,048,576 robots per GPU: the hand-over list is many waves long and takes the split "
+                                                               "blending path (classification kernel, one variant per warp); 10 cycles, CUDA events"})},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
