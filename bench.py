@@ -41,6 +41,7 @@ METRIC = "robot_control_cycles_per_sec"
 UNIT = "cycles/s"
 FLOP_PER_CYCLE = 9.5e3
 FP64_PEAK_TFLOPS = 37.2       # 148 SM x 64 FMA/clk x 2 x 1.965 GHz (no FP64 entry in MEASURED_PEAKS.json)
+FP32_PEAK_TFLOPS = 74.4       # 148 SM x 128 FMA/clk x 2 x 1.965 GHz (optional FP32 mode, reported separately)
 WORKLOAD = "config2: Panda MotionForceTask 6-DoF + JointTask null space via RobotController, OTG off, BIE decoupling (reference defaults)"
 ROBOT = "panda"
 LINK, POINT = "end-effector", (0.0, 0.0, 0.07)
@@ -606,11 +607,60 @@ def gpu_arm(args):
             fp64_measured = float(t_.value)
     barrier()
 
+    # ---- the optional single-precision mode (north star: "held to 1e-4 relative and reported separately"): the same controller
+    # instances and cycles with the fused kernel in FP32 (state, goals, integrators and torques stay FP64 in HBM), and its
+    # error against the FP64 mode on a fresh pair of 4,096-robot batches (same states, same goals, 3 cycles each)
+    fp32_ms, fp32_err = float("nan"), float("nan")
+    if R >= 4096 and all(lib.osc_set_precision(s_["robot"].handle, capi.OSC_PRECISION_FP32) == 0 for s_ in sets):
+        for s_ in sets:
+            s_["robot"].setStream(stream.cuda_stream)     # the instances were on their own streams for the sections above
+        torch.cuda.set_stream(stream)
+        f_steps = max(args.steps, 100)
+        for w in range(8):
+            step_device(sets[w % n_sets])
+        barrier()
+        f_runs = []
+        for _ in range(5):
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            f0.record()
+            for k in range(f_steps):
+                step_device(sets[k % n_sets])
+            f1.record()
+            barrier()
+            f_runs.append(f0.elapsed_time(f1) / f_steps)
+        fp32_ms = float(np.median(f_runs))
+        if (sets[0]["robot"].status() & (capi.STATUS_UNHANDLED | capi.STATUS_SINGULAR_PATH)).any() or not bool(torch.isfinite(sets[0]["tau"]).all()):
+            raise SystemExit("bench: FP32 mode left the fused kernel or produced non-finite torques")
+        for s_ in sets:
+            lib.osc_set_precision(s_["robot"].handle, capi.OSC_PRECISION_FP64)
+        pair = {}
+        for mode in (capi.OSC_PRECISION_FP64, capi.OSC_PRECISION_FP32):
+            probot = sp.BatchedRobot(ROBOT, 4096, device=local_rank)
+            probot.setStream(stream.cuda_stream)
+            probot.setQ(q[:4096]); probot.setDq(dq[:4096]); probot.updateModel()
+            pm = sp.MotionForceTask(probot, LINK, (np.eye(3), np.array(POINT))); pj = sp.JointTask(probot)
+            pm.disableInternalOtg(); pj.disableInternalOtg()
+            pc = sp.RobotController(probot, [pm, pj])
+            pm.setGoalPosition(goals["xd"][:4096]); pm.setGoalOrientation(goals["Rd"][:4096]); pm.setGoalLinearVelocity(goals["vd"][:4096])
+            pm.setGoalAngularVelocity(goals["wd"][:4096]); pm.setGoalLinearAcceleration(goals["ad"][:4096]); pm.setGoalAngularAcceleration(goals["ald"][:4096])
+            pj.setGoalPosition(goals["qd"][:4096])
+            lib.osc_set_precision(probot.handle, mode)
+            for _ in range(3):
+                pc.updateControllerTaskModels()
+                ptau = pc.computeControlTorques()
+            pair[mode] = ptau
+            del pc
+            probot.close()
+        ref64 = pair[capi.OSC_PRECISION_FP64]
+        fp32_err = float((np.abs(pair[capi.OSC_PRECISION_FP32] - ref64).max(axis=1) / np.maximum(np.abs(ref64).max(axis=1), 1e-9)).max())
+    barrier()
+
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([e2e_ms, multi_ms, link_ms, unfiltered_ms, unfiltered_large_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_ms, multi_ms, link_ms, unfiltered_ms, unfiltered_large_ms, fp32_ms, fp32_err], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms, multi_ms, link_ms, unfiltered_ms, unfiltered_large_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
+        e2e_ms, multi_ms, link_ms, unfiltered_ms, unfiltered_large_ms, fp32_ms, fp32_err = (float(t[k]) for k in range(7))
     value = world * R * args.steps / (total_ms * 1e-3)
     e2e_value = world * R * e2e_steps / (e2e_ms * 1e-3)
 
@@ -658,6 +708,14 @@ def gpu_arm(args):
                                             "robots_on_the_general_path": unfiltered_singular,
                                             "what": "same hierarchy and batch size, uniformly sampled states without the s_min/s_max filter: the "
                                                     "robots inside the reference's blending band take the general (SVD) path; 30 cycles, CUDA events"},
+                      "fp32_mode": (None if not (fp32_ms == fp32_ms) else
+                                    {"value": world * R / (fp32_ms * 1e-3), "unit": UNIT, "ms_per_step": fp32_ms, "dtype": "f32",
+                                     "max_relative_error_vs_fp64": fp32_err, "tolerance": 1e-4,
+                                     "fraction_of_fp32_roofline": FLOP_PER_CYCLE * R / (fp32_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+                                     "what": "optional single-precision mode (osc_set_precision): the same instances and cycles with the fused kernel in FP32 "
+                                             "arithmetic on FP64 state; reported separately, not part of `value`; the error is per robot, "
+                                             "max |tau32 - tau64| / max |tau64|, 4,096 robots, third cycle; roofline against %.1f TFLOP/s FP32 "
+                                             "(148 SM x 128 FMA/clk x 2 x 1.965 GHz)" % FP32_PEAK_TFLOPS}),
                       "unfiltered_states_1m_robots": (None if not (unfiltered_large_ms == unfiltered_large_ms) else
                                                       {"value": world * R_LARGE / (unfiltered_large_ms * 1e-3), "unit": UNIT, "ms_per_step": unfiltered_large_ms,
                                                        "robots_per_gpu": R_LARGE, "robots_on_the_general_path": unfiltered_large_singular,

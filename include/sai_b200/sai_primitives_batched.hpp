@@ -461,6 +461,9 @@ public:
 	}
 	// setQ/setDq/updateModel + updateControllerTaskModels + computeControlTorques in one launch
 	void step(const double* q, const double* dq, double* tau, osc_mem_kind where) { check(_robot->handle(), osc_step(_robot->handle(), q, dq, tau, where)); }
+	// optional single-precision mode of the fused kernel (no reference counterpart; sai_b200_osc.h, osc_set_precision)
+	void setPrecision(osc_precision precision) { check(_robot->handle(), osc_set_precision(_robot->handle(), precision)); }
+	osc_precision getPrecision() const { return (osc_precision)osc_get_precision(_robot->handle()); }
 	void enableGravityCompensation(bool on) { check(_robot->handle(), osc_enable_gravity_compensation(_robot->handle(), on)); }
 	void enableJointLimitAvoidance(bool on) { check(_robot->handle(), osc_enable_joint_limit_avoidance(_robot->handle(), on)); }
 	void enableTorqueSaturation(bool on) { check(_robot->handle(), osc_enable_torque_saturation(_robot->handle(), on)); }

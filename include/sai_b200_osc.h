@@ -356,6 +356,17 @@ int64_t osc_launch_count(const osc_handle* h);
 int osc_debug_popc_sequence(osc_handle* h, int task_id, int n_steps, const double* fd, const double* fs, const double* vcl,
 							const double* vr, double kv_force, double kff_force, double* out);
 
+/* ---- optional single-precision mode (BASELINE.json north_star: "an optional FP32 mode is held to 1e-4 relative and reported
+ * separately"; the reference itself is double precision throughout, e.g. RobotController.cpp:75-120).  OSC_PRECISION_FP32 runs
+ * the fused kernel of the flagship hierarchy -- a full six-dof MotionForceTask under pure motion control, alone or with a full
+ * JointTask in its null space, on a robot whose joints are all revolute about their local z axis (seven joints compiled in) --
+ * in FP32 arithmetic.  All data in device memory (state, goals, integrators, torques) stay FP64, and robots inside the
+ * singularity band continue on the FP64 general path.  A hierarchy outside that description makes
+ * osc_compute_control_torques / osc_step return OSC_ERR_UNSUPPORTED while the mode is on; there is no silent fallback. ---- */
+typedef enum { OSC_PRECISION_FP64 = 0, OSC_PRECISION_FP32 = 1 } osc_precision;
+int osc_set_precision(osc_handle* h, int precision);
+int osc_get_precision(osc_handle* h);
+
 /* ---- measurement aid (no reference counterpart): %globaltimer stamps of every block of the fused kernel over the last 8 cycles,
  * so that the overlap of consecutive cycles can be looked at (tools/pipeline_trace.py).  out == NULL: switch the stamps on / off;
  * out != NULL: read back [cycle & 7][block][start, end] (nanoseconds).  Returns the number of blocks per cycle. ---- */

@@ -636,6 +636,16 @@ class RobotController:
     def stepDevice(self, q_ptr, dq_ptr, tau_ptr):
         _check(self._robot.handle, self._lib.osc_step(self._robot.handle, C.c_void_p(q_ptr), C.c_void_p(dq_ptr), C.c_void_p(tau_ptr), capi.OSC_MEM_DEVICE))
 
+    def setPrecision(self, precision):
+        """osc_set_precision (no reference counterpart: the reference is double precision): "fp64" (default) or "fp32" -- the optional
+        single-precision mode of the fused kernel, for a full six-dof MotionForceTask under pure motion control with or without a
+        full JointTask; any other hierarchy raises on the next computeControlTorques while it is on"""
+        code = {"fp64": capi.OSC_PRECISION_FP64, "fp32": capi.OSC_PRECISION_FP32}[precision]
+        _check(self._robot.handle, self._lib.osc_set_precision(self._robot.handle, code))
+
+    def getPrecision(self):
+        return "fp32" if self._lib.osc_get_precision(self._robot.handle) == capi.OSC_PRECISION_FP32 else "fp64"
+
     def enableGravityCompensation(self, flag):
         _check(self._robot.handle, self._lib.osc_enable_gravity_compensation(self._robot.handle, 1 if flag else 0))
 

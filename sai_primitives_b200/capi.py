@@ -28,6 +28,7 @@ OSC_ERR_STATE = -5
 
 OSC_MEM_HOST = 0
 OSC_MEM_DEVICE = 1
+OSC_PRECISION_FP64, OSC_PRECISION_FP32 = 0, 1
 
 FULL_DYNAMIC_DECOUPLING = 0
 BOUNDED_INERTIA_ESTIMATES = 1
@@ -214,6 +215,8 @@ SYMBOLS = {
     "osc_measure_fp64_peak": (C.c_int, [_H, C.c_double, _PD]),
     "osc_debug_block_times": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
     "osc_debug_general_path_counts": (C.c_int, [_H, C.POINTER(C.c_int32)]),
+    "osc_set_precision": (C.c_int, [_H, C.c_int]),
+    "osc_get_precision": (C.c_int, [_H]),
     "osc_sim_integrate": (C.c_int, [_H, _PD, _PD, _PD, C.c_double, C.c_int, C.c_int]),
     "osc_eval_model": (C.c_int, [_H, C.c_int, C.POINTER(LinkFrame), C.POINTER(D), _PD, _PD, _PD, _PD, _PD, C.c_int]),
 }

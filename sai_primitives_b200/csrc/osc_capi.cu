@@ -1137,6 +1137,20 @@ int osc_enable_joint_limit_avoidance(osc_handle* h, int enabled) {
 	return OSC_OK;
 }
 
+int osc_set_precision(osc_handle* h, int precision) {
+	ENTER(h);
+	if (precision != OSC_PRECISION_FP64 && precision != OSC_PRECISION_FP32) return fail(h, OSC_ERR_INVALID_ARGUMENT, "precision must be OSC_PRECISION_FP64 or OSC_PRECISION_FP32");
+	if (precision == OSC_PRECISION_FP32 && !osc::fused_f32_available(h->model.n))
+		return fail(h, OSC_ERR_UNSUPPORTED, "FP32 mode: no single-precision kernel compiled for this robot dof");
+	h->prog.precision_fp32 = (precision == OSC_PRECISION_FP32) ? 1 : 0;
+	return OSC_OK;
+}
+
+int osc_get_precision(osc_handle* h) {
+	ENTER(h);
+	return h->prog.precision_fp32 ? OSC_PRECISION_FP32 : OSC_PRECISION_FP64;
+}
+
 int osc_debug_general_path_counts(osc_handle* h, int32_t* out4) {
 	ENTER(h);
 	if (!out4) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null output");
@@ -1192,6 +1206,12 @@ static int run_cycle(osc_handle* h, double* tau_out, int mem_kind, bool sync_hos
 	if (!h->finalized) return fail(h, OSC_ERR_STATE, "controller not finalized");
 	if (!tau_out) return fail(h, OSC_ERR_INVALID_ARGUMENT, "null torque output");
 	if (mem_kind != OSC_MEM_HOST && mem_kind != OSC_MEM_DEVICE) return fail(h, OSC_ERR_INVALID_ARGUMENT, "bad mem_kind");
+	if (h->prog.precision_fp32) {  // decided before anything is launched or counted: a refused cycle leaves the handle as it was
+		bool motion = false;
+		if (!(h->sig_R == 6 && h->prog.mft[0].full && osc::cycle_spec_eligible(h->prog, h->sig_jt, &motion) && motion && osc::fused_f32_available(h->model.n)))
+			return fail(h, OSC_ERR_UNSUPPORTED,
+						"FP32 mode covers a full six-dof MotionForceTask under pure motion control (alone or with a full JointTask) on an all-revolute-z chain only");
+	}
 	h->prog.tau = (mem_kind == OSC_MEM_DEVICE) ? tau_out : h->d_tau;
 	h->prog.update_models = h->models_armed ? 1 : 0;
 	h->models_armed = false;

@@ -182,7 +182,7 @@ DEVI void park_for_blend(const OscProgram& P, int slot, int64_t i, const double 
 						 const double (&grav)[N], const SmTri<N, kCycleBlock>& Ls, const double* Js) {
 	using BL = BlendLayout<N>;
 	const int64_t cap = P.blend_cap, NR = P.n_robots;
-	double* S = P.blend_scratch + slot;
+	gdouble* S = P.blend_scratch + slot;
 	constexpr int sms = kCycleBlock;
 #pragma unroll
 	for (int j = 0; j < N; j++) {

@@ -18,6 +18,7 @@ bool cycle_signature_available(int n, int R, bool has_jt) {
 
 cudaError_t launch_cycle(int n, int R, bool has_jt, const OscProgram& P, cudaStream_t stream) {
 	if (!cycle_signature_available(n, R, has_jt)) return cudaErrorNotSupported;
+	if (P.precision_fp32 && R != 6) return cudaErrorNotSupported;  // the single-precision mode covers the full six-dof task only (osc_cycle_f32.cu)
 #define CALL(m) \
 	if (n == m) return launch_cycle_n##m(R, has_jt, P, stream);
 	OSC_CYCLE_DOFS(CALL)

@@ -24,57 +24,6 @@
 
 namespace osc {
 
-// smallest eigenvalue of a symmetric 3 x 3 matrix (xx xy xz yy yz zz), trigonometric closed form
-static double min_eig_sym3(const double* I) {
-	const double a = I[0], b = I[3], c = I[5], d = I[1], e = I[2], f = I[4];
-	const double p1 = d * d + e * e + f * f;
-	const double q = (a + b + c) / 3.0;
-	if (p1 == 0.0) return std::min(a, std::min(b, c));
-	const double p2 = (a - q) * (a - q) + (b - q) * (b - q) + (c - q) * (c - q) + 2.0 * p1;
-	const double p = std::sqrt(p2 / 6.0);
-	const double B[6] = {(a - q) / p, d / p, e / p, (b - q) / p, f / p, (c - q) / p};
-	double r = 0.5 * (B[0] * (B[3] * B[5] - B[4] * B[4]) - B[1] * (B[1] * B[5] - B[4] * B[2]) + B[2] * (B[1] * B[4] - B[3] * B[2]));
-	r = std::max(-1.0, std::min(1.0, r));
-	const double phi = std::acos(r) / 3.0;
-	return q + 2.0 * p * std::cos(phi + 2.0 * 3.14159265358979323846 / 3.0);
-}
-
-// Conditions under which the specialised instantiation (SPEC, osc_cycle.cuh) computes the same thing as the general one.
-// *motion: the motion-force task additionally is a full task under pure motion control (the MOTION flag of the kernel)
-static bool cycle_spec_eligible(const OscProgram& P, bool has_jt, bool* motion) {
-	const DevModel& m = P.model;
-	for (int j = 0; j < m.n; j++)
-		if (m.jtype[j] != 0 || m.axis[j][0] != 0.0 || m.axis[j][1] != 0.0 || m.axis[j][2] != 1.0) return false;
-	if (P.mft[0].body < 0) return false;
-	if ((unsigned long long)P.n_robots * (unsigned long long)MC_COUNT >= (1ull << 32)) return false;  // 32-bit element indices
-	// The specialisation carries the bounded-inertia update of rank <= 1 only (robots needing more are handed to the
-	// general path one by one, which is correct but slow): require that at most one diagonal entry of M can ever fall
-	// below the threshold.  M_jj >= sum over the bodies the joint moves of their smallest principal moment of inertia.
-	{
-		double thr = 0.0;
-		if (P.mft[0].p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES) thr = std::max(thr, P.mft[0].p.bie_threshold);
-		if (has_jt && P.jt[0].p.dynamic_decoupling_type == OSC_BOUNDED_INERTIA_ESTIMATES) thr = std::max(thr, P.jt[0].p.bie_threshold);
-		double lb = 0.0;
-		int may_clamp = 0;
-		for (int j = m.n - 1; j >= 0; j--) {
-			lb += min_eig_sym3(m.inertia[j]);
-			if (lb < thr) may_clamp++;
-		}
-		if (may_clamp > 1) return false;
-	}
-	const DevMft& t = P.mft[0];
-	const osc_mft_params& p = t.p;
-	// IMPEDANCE decoupling needs no code of its own (Lambda_modified = I: the solves are skipped); velocity saturation of the
-	// motion-force task is part of the general control law, which the structural specialisation (MOTION = false) keeps
-	*motion = t.full && p.force_space_dimension == 0 && p.moment_space_dimension == 0 && !p.closed_loop_force_control &&
-			  !p.closed_loop_moment_control && !p.use_velocity_saturation;
-	if (has_jt) {
-		const DevJt& j = P.jt[0];
-		if (!j.full || j.p.use_velocity_saturation) return false;  // the staged joint control law has no velocity saturation
-	}
-	return true;
-}
-
 // multiprocessors of the current device (cached per device)
 static int sm_count() {
 	static std::atomic<int> cached[64];
@@ -151,7 +100,11 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 		const bool spec = cycle_spec_eligible(P, JT, &motion);
 		// with many robots on the general path the hand-overs also park their kinematics and dynamics for the split blending path
 		const bool park = P.mft[0].full && blend_split_selected(P);
-		if (!P.mft[0].full)
+		if (P.precision_fp32) {
+			// optional single-precision mode: only the specialised pure-motion kernel has an FP32 instantiation (osc_cycle_f32.cu)
+			if (!(P.mft[0].full && spec && motion)) return cudaErrorNotSupported;
+			e0 = launch_cycle_fused_f32(N, JT, P, stream);
+		} else if (!P.mft[0].full)
 			e0 = launch_variant<N, R, JT, false>(P, stream);
 		else if (spec && motion && !park)
 			e0 = P.gravity_comp ? launch_variant<N, R, JT, true, true, true>(P, stream) : launch_variant<N, R, JT, true, true, false>(P, stream);

@@ -6,6 +6,10 @@
 
 #include "../../include/sai_b200_osc.h"
 
+// element type of the arrays in global memory (inputs, task state, torques): FP64 also in the single-precision
+// instantiation of the kernels (gen_fp32.py rewrites `double`, not this)
+typedef double gdouble;
+
 // ---- SoA component layout of the per-robot MotionForceTask state block ----
 enum MftComp : int {
 	MC_GOAL_POS = 0,	  // 3
@@ -170,4 +174,5 @@ struct OscProgram {
 	int32_t* blend_counts;	// [0..3] list counters, [4..7] those of the last cycle (osc_debug_general_path_counts)
 	int64_t blend_cap;
 	int32_t blend_split_on;	 // host decision for this cycle (the hint says many robots are on the general path)
+	int32_t precision_fp32;	 // osc_set_precision: the fused kernel of the flagship hierarchy runs in single precision
 };

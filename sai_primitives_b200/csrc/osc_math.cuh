@@ -44,6 +44,7 @@ DEVI void mat3_mul_bt(const double A[9], const double B[9], double C[9]) {
 			C[3 * i + j] = A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1] + A[3 * i + 2] * B[3 * j + 2];
 }
 
+#ifndef OSC_FP32_BUILD
 // ---- lean FP64 reciprocal / reciprocal square root / sine-cosine --------------------------------------------------
 // The CUDA library versions carry special-case branches (subnormals, infinities, huge arguments) that cost a
 // predicate test, a convergence barrier and a cold subroutine per call site: about 35 instructions for rsqrt(), 80 for
@@ -127,6 +128,35 @@ DEVI void cp_async8(double* smem_dst, const double* gsrc) {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
 }
 DEVI void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#else
+// the same routines for the single-precision instantiation (gen_fp32.py copies this region verbatim): hardware seed plus
+// one Newton step (about 1 ulp), the library sine-cosine, and a plain converting load in place of the 8-byte cp.async
+DEVI float rsqrt_pos(float d) {
+	float y;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
+	const float e = fmaf(-d * y, y, 1.0f);
+	return fmaf(y * e, 0.5f, y);
+}
+DEVI float rcp_nz(float d) {
+	float y;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
+	const float e = fmaf(-d, y, 1.0f);
+	return fmaf(y, e, y);
+}
+DEVI float sqrt_pos(float d) {
+	const float y = rsqrt_pos(d);
+	const float s = d * y;
+	return fmaf(fmaf(-s, s, d), 0.5f * y, s);
+}
+DEVI float div_nz(float a, float b) {
+	const float y = rcp_nz(b);
+	const float q = a * y;
+	return fmaf(fmaf(-b, q, a), y, q);
+}
+DEVI void sincos_joint(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
+DEVI void cp_async8(float* smem_dst, const gdouble* gsrc) { *smem_dst = (float)*gsrc; }
+DEVI void cp_async_wait_all() {}
+#endif  // OSC_FP32_BUILD
 
 // In-place Cholesky of the lower triangle of a symmetric positive definite matrix: A = L L^T.
 // invd[j] = 1 / L[j][j] is kept so that the triangular solves multiply instead of divide (one FP64 reciprocal

@@ -16,13 +16,13 @@ namespace osc {
 #define ST(comp, c) st[(decltype(NR))((comp) + (c)) * NR + i]
 
 template <typename IDX>
-DEVI void load3(const double* st, IDX NR, IDX i, int comp, double v[3]) {
+DEVI void load3(const gdouble* st, IDX NR, IDX i, int comp, double v[3]) {
 	v[0] = ST(comp, 0);
 	v[1] = ST(comp, 1);
 	v[2] = ST(comp, 2);
 }
 template <typename IDX>
-DEVI void store3(double* st, IDX NR, IDX i, int comp, const double v[3]) {
+DEVI void store3(gdouble* st, IDX NR, IDX i, int comp, const double v[3]) {
 	ST(comp, 0) = v[0];
 	ST(comp, 1) = v[1];
 	ST(comp, 2) = v[2];
@@ -83,7 +83,7 @@ DEVI void sigma_complement(const double P[9], const double S[9], double C[9]) {
 template <typename IDX>
 DEVI void popc_step(const DevMft& t, IDX NR, IDX i, const double fd[3], const double fs[3], const double vcl[3],
 					const double vr[3], double kv, double kff, double out[3], uint32_t& status) {
-	double* st = t.st;
+	gdouble* st = t.st;
 	int32_t* ist = t.ist;
 	if (!t.p.passivity_enabled) {
 #pragma unroll
@@ -180,7 +180,7 @@ DEVI double pinv_gain(double k) { return (k > 1e-6) ? 1.0 / k : 0.0; }
 // MC_INT_POS, MC_INT_ORI) were staged into shared memory (element e at sg[e * sgs]) by mft_stage_goals.
 template <typename IDX>
 DEVI void mft_stage_goals(const DevMft& t, IDX NR, IDX i, double* sg, int sgs) {
-	const double* st = t.st;
+	const gdouble* st = t.st;
 #pragma unroll
 	for (int c = 0; c < 24; c++) cp_async8(sg + c * sgs, &ST(MC_GOAL_POS, c));
 #pragma unroll
@@ -190,7 +190,7 @@ template <bool MOTION = false, typename IDX = int64_t>
 DEVI bool mft_control_law(const DevMft& t, IDX NR, IDX i, const double x[3], const double R[9], const double v_in[3],
 						  const double w_in[3], bool write_observers, double fstar[6], double F[6], uint32_t& status,
 						  const double* sg = nullptr, int sgs = 0) {
-	double* st = t.st;
+	gdouble* st = t.st;
 	const osc_mft_params& p = t.p;
 	const double dt = t.dt;
 	double v[3] = {v_in[0], v_in[1], v_in[2]}, w[3] = {w_in[0], w_in[1], w_in[2]};
@@ -471,8 +471,8 @@ DEVI bool mft_control_law(const DevMft& t, IDX NR, IDX i, const double x[3], con
 // staged variant: goals (position, velocity, acceleration), integrator, q and dq of the robot, 6 N doubles, copied to
 // shared memory ahead of time (element e at sg[e * sgs])
 template <int N, typename IDX>
-DEVI void joint_stage_goals(const DevJt& t, const double* qg, const double* dqg, IDX NR, IDX i, double* sg, int sgs) {
-	const double* st = t.st;
+DEVI void joint_stage_goals(const DevJt& t, const gdouble* qg, const gdouble* dqg, IDX NR, IDX i, double* sg, int sgs) {
+	const gdouble* st = t.st;
 #pragma unroll
 	for (int a = 0; a < N; a++) {
 		cp_async8(sg + a * sgs, &ST(JC_GOAL_POS, a));
@@ -486,7 +486,7 @@ DEVI void joint_stage_goals(const DevJt& t, const double* qg, const double* dqg,
 // full joint task without velocity saturation from the staged copy (the SPEC instantiation)
 template <int N, typename IDX>
 DEVI void joint_control_law_staged(const DevJt& t, IDX NR, IDX i, const double* sg, int sgs, double (&pid)[N], double (&acc)[N]) {
-	double* st = t.st;
+	gdouble* st = t.st;
 	const osc_joint_params& p = t.p;
 	cp_async_wait_all();
 	double I[N];
@@ -504,7 +504,7 @@ DEVI void joint_control_law_staged(const DevJt& t, IDX NR, IDX i, const double* 
 template <int N, int K, bool SPEC = false, typename IDX = int64_t>  // SPEC: full selection, no velocity saturation (host check)
 DEVI void joint_control_law(const DevJt& t, IDX NR, IDX i, const double (&q)[N], const double (&dq)[N],
 							double (&pid)[K], double (&acc)[K]) {
-	double* st = t.st;
+	gdouble* st = t.st;
 	const osc_joint_params& p = t.p;
 	// all loads first, all stores last: the compiler cannot prove that the integrator stores do not alias the
 	// following goal loads, and would otherwise serialise one memory round trip per task coordinate
@@ -553,7 +553,7 @@ DEVI void joint_control_law(const DevJt& t, IDX NR, IDX i, const double (&q)[N],
 template <int N>
 static __device__ __noinline__ void joint_control_law_rt(const DevJt& t, int64_t NR, int64_t i, const double (&q)[N], const double (&dq)[N], int k,
 														  double* pid, double* acc) {
-	double* st = t.st;
+	gdouble* st = t.st;
 	const osc_joint_params& p = t.p;
 	for (int a = 0; a < k; a++) {
 		double pos = 0.0, vel = 0.0;
