@@ -10,7 +10,7 @@ import json
 for f in ("20", "1000"):
     d = json.loads(open("gpurun_out/r02_final_bench_%s.json" % f).read().strip().splitlines()[-1])
     print(f, "value %.4g frac %.4f" % (d["value"], d["roofline"]["frac"]), "lat", d["latency_ms"]["p50"], "e2e %.4g" % d["e2e"]["value"], "launches", d["gpu_launches"],
-          "unfiltered %.4g" % d["extra"]["unfiltered_states"]["value"], "1M %.4g" % d["extra"]["unfiltered_states_1m_robots"]["value"], d.get("cpu_baseline", {}).get("value"))
+          "unfiltered %.4g" % d["extra"]["unfiltered_states"]["value"], "1M %.4g" % d["extra"]["unfiltered_states_1m_robots"]["value"], (d.get("cpu_baseline") or {}).get("value"))
 d = json.loads(open("gpurun_out/r02_final_bench_ref.json").read().strip().splitlines()[-1])
 print("reference arm", d["value"], d["unit"], d["cpu_baseline"]["kind"], d["cpu_baseline"]["cores"])
 PY
