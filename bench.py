@@ -630,7 +630,9 @@ def gpu_arm(args):
             barrier()
             f_runs.append(f0.elapsed_time(f1) / f_steps)
         fp32_ms = float(np.median(f_runs))
-        if (sets[0]["robot"].status() & (capi.STATUS_UNHANDLED | capi.STATUS_SINGULAR_PATH)).any() or not bool(torch.isfinite(sets[0]["tau"]).all()):
+        fst = sets[0]["robot"].status()
+        if (fst & capi.STATUS_UNHANDLED).any() or not bool(torch.isfinite(sets[0]["tau"]).all()) or \
+                (args.min_ratio > 0 and (fst & capi.STATUS_SINGULAR_PATH).any()):
             raise SystemExit("bench: FP32 mode left the fused kernel or produced non-finite torques")
         for s_ in sets:
             lib.osc_set_precision(s_["robot"].handle, capi.OSC_PRECISION_FP64)

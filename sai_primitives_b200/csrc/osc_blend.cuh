@@ -101,6 +101,9 @@ struct BlendScratchSource {
 // SMEM: the factor L and the matrix T (70 of the doubles with the longest lives) are kept in shared memory, element e of
 // this thread at smem[e * kBlendBlock], instead of registers (where, with everything else, they spill).
 constexpr int kBlendBlock = 64;
+// measured: with L and T in shared memory the variants kernel is 2 % slower (143 KB of shared memory per SM leave the spills
+// 100 KB of L1 instead of 240 KB), so the split path runs with SMEM off; the switch stays for the next restructuring
+constexpr bool kBlendSmem = false;
 template <int N>
 constexpr int blend_smem_doubles() {
 	return N * (N + 1) / 2 + 6 * N;
@@ -877,7 +880,7 @@ DEVI void blend_variant(const OscProgram& P, const int64_t i, const int64_t slot
 #pragma unroll
 	for (int k = 0; k < 9; k++) Rc[k] = src.at(BL::RC + k);
 	const double alpha = src.at(BL::ALPHA);
-	if (!blend_path<N, NS, HAS_JT, BlendScratchSource<N>, MOTION, true>(P, i, q, dq, src, sig, alpha, x, Rc, OSC_STATUS_SINGULAR_PATH, sm)) {
+	if (!blend_path<N, NS, HAS_JT, BlendScratchSource<N>, MOTION, kBlendSmem>(P, i, q, dq, src, sig, alpha, x, Rc, OSC_STATUS_SINGULAR_PATH, sm)) {
 		// cannot happen: blend_classify sends every case blend_path refuses to the general path before any state is touched
 		const int64_t NR = P.n_robots;
 #pragma unroll
@@ -936,8 +939,8 @@ template <int N, bool HAS_JT, bool MOTION>
 __global__ void __launch_bounds__(kBlendBlock) osc_blend_variants_kernel(const __grid_constant__ OscProgram P) {
 	asm volatile("griddepcontrol.launch_dependents;");
 	asm volatile("griddepcontrol.wait;" ::: "memory");
-	extern __shared__ double blend_sm[];  // blend_smem_doubles<N>() per thread
-	double* sm = blend_sm + threadIdx.x;
+	extern __shared__ double blend_sm[];  // blend_smem_doubles<N>() per thread when kBlendSmem
+	double* sm = kBlendSmem ? blend_sm + threadIdx.x : nullptr;
 	const int32_t c0 = P.blend_counts[0], c1 = P.blend_counts[1], c2 = P.blend_counts[2];
 	const int bs = (int)blockDim.x;
 	const int b1 = (c1 + bs - 1) / bs, b2 = (c2 + bs - 1) / bs, b0 = (c0 + bs - 1) / bs;

@@ -156,7 +156,7 @@ static cudaError_t launch_one(const OscProgram& P, cudaStream_t stream) {
 				const osc_mft_params& mp = P.mft[0].p;
 				const bool motion = mp.force_space_dimension == 0 && mp.moment_space_dimension == 0 && !mp.closed_loop_force_control &&
 									!mp.closed_loop_moment_control && !mp.use_velocity_saturation;
-				constexpr int vsmem = blend_smem_doubles<N>() * kBlendBlock * (int)sizeof(double);
+				constexpr int vsmem = kBlendSmem ? blend_smem_doubles<N>() * kBlendBlock * (int)sizeof(double) : 0;
 				static_assert(vsmem <= 48 * 1024, "variants kernel: dynamic shared memory beyond the default limit");
 				static std::atomic<int> per_sm[64][3];
 				int dev = 0;
