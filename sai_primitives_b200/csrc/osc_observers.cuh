@@ -62,7 +62,7 @@ static __device__ __noinline__ void task_nullspace_one(const OscProgram& P, cons
 		mm(J0, 6, n, Nprec, n, J);
 		constexpr int K = (N < 6) ? N : 6;
 		double U[6 * K], sv[K], V[N * K];
-		svd_thin(J, 6, n, U, sv, V);
+		svd_rows6(J, n, U, sv, V);
 		int n_ns = 0, n_s = 0;
 		if (sv[0] < p.s_abs_tol) {
 			n_s = r;

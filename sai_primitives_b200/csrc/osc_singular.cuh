@@ -11,6 +11,8 @@
 #include "osc_kindyn.cuh"
 #include "osc_pipeline.cuh"
 #include "osc_tasks.cuh"
+#define OSC_EIG6_LEAN_MATH
+#include "osc_eig6.h"
 
 #ifndef OSC_GENERIC_MIN_BLOCKS
 #define OSC_GENERIC_MIN_BLOCKS 4
@@ -217,6 +219,71 @@ static __device__ __noinline__ void svd_thin(const double* A, int m, int n, doub
 	}
 }
 
+// Thin SVD of the six-row projected task Jacobian A (6 x n, row-major), k = min(6, n):  A = U diag(s) V^T through the
+// eigen-decomposition of the 6 x 6 Gram matrix A A^T in registers (osc_eig6.h), V = A^T U / s -- what the blending path does
+// (osc_blend.cuh), a tenth of the instructions of the one-sided Jacobi above on this shape (it was a third of the rolled general
+// path: profiles/r02_summary.md).  Same conventions: s descending, a zero singular value gets a zero column of V, the
+// largest-magnitude entry of every column of V is positive.
+static __device__ __noinline__ void svd_rows6(const double* A, int n, double* U, double* s, double* V) {
+	const int k = n < 6 ? n : 6;
+	double G[6][6], Z[6][6], d[6];
+#pragma unroll
+	for (int a = 0; a < 6; a++)
+#pragma unroll
+		for (int b = 0; b <= a; b++) {
+			double t = 0.0;
+			for (int j = 0; j < n; j++) t += A[a * n + j] * A[b * n + j];
+			G[a][b] = t;
+			G[b][a] = t;
+		}
+	sym_eig6(G, Z, d);
+#pragma unroll
+	for (int a = 0; a < 5; a++)
+#pragma unroll
+		for (int b = a + 1; b < 6; b++) {
+			if (d[b] > d[a]) {
+				const double td = d[a];
+				d[a] = d[b];
+				d[b] = td;
+#pragma unroll
+				for (int r = 0; r < 6; r++) {
+					const double tz = Z[r][a];
+					Z[r][a] = Z[r][b];
+					Z[r][b] = tz;
+				}
+			}
+		}
+#pragma unroll
+	for (int jj = 0; jj < 6; jj++) {
+		if (jj < k) {
+			const double sv = sqrt(fmax(d[jj], 0.0));
+			s[jj] = sv;
+			const double inv = sv > 0.0 ? 1.0 / sv : 0.0;
+#pragma unroll
+			for (int a = 0; a < 6; a++) U[a * k + jj] = Z[a][jj];
+			int im = 0;
+			double vm = 0.0;
+			for (int i = 0; i < n; i++) {
+				double t = 0.0;
+#pragma unroll
+				for (int a = 0; a < 6; a++) t += A[a * n + i] * Z[a][jj];
+				t *= inv;
+				V[i * k + jj] = t;
+				if (fabs(t) > fabs(vm)) {
+					vm = t;
+					im = i;
+				}
+			}
+			(void)im;
+			if (vm < 0.0) {
+				for (int i = 0; i < n; i++) V[i * k + jj] = -V[i * k + jj];
+#pragma unroll
+				for (int a = 0; a < 6; a++) U[a * k + jj] = -U[a * k + jj];
+			}
+		}
+	}
+}
+
 // SaiModel::operationalSpaceMatrices(J) for J (r x n): Lambda (r x r), N (n x n); Jbar is not needed by the callers
 static __device__ __noinline__ void op_space(const double* J, int r, int n, const double* Minv, double* Lambda, double* Nout) {
 	double MJt[MAXD * MAXD], A[MAXD * MAXD], Jbar[MAXD * MAXD];
@@ -302,7 +369,7 @@ static __device__ __noinline__ void generic_cycle_one(const OscProgram& P, const
 			// ---- SingularityHandler::updateTaskModel (:75-228)
 			constexpr int K = (N < 6) ? N : 6;	// thin SVD width
 			double U[6 * K], sv[K], V[N * K];
-			svd_thin(J, 6, n, U, sv, V);
+			svd_rows6(J, n, U, sv, V);
 			int n_ns = 0, n_s = 0;	// columns of the non-singular / singular task range
 			double alpha = 1.0;
 			if (sv[0] < p.s_abs_tol) {	// fully singular (:83-98)
