@@ -27,42 +27,45 @@ namespace osc {
 #define EIG6_RCP(x) (1.0 / (x))
 #endif
 
-// A (symmetric, both triangles filled; destroyed) = Z diag(d) Z^T, eigenvalues in no particular order.
-EIG6_HD void sym_eig6(double (&A)[6][6], double (&Z)[6][6], double (&d)[6]) {
+// A (symmetric M x M, both triangles filled; destroyed) = Z diag(d) Z^T, eigenvalues in no particular order.  M = 6 is the Gram
+// matrix of the task Jacobian; the rolled general path also uses M = number of joints for the range basis of the joint task's
+// projected Jacobian (osc_singular.cuh).
+template <int M>
+EIG6_HD void sym_eig(double (&A)[M][M], double (&Z)[M][M], double (&d)[M]) {
 	constexpr double kTiny = 1e-290, kEps = 1.1102230246251565e-16;
-	double e[6];
+	double e[M];
 #pragma unroll
-	for (int a = 0; a < 6; a++)
+	for (int a = 0; a < M; a++)
 #pragma unroll
-		for (int b = 0; b < 6; b++) Z[a][b] = (a == b) ? 1.0 : 0.0;
+		for (int b = 0; b < M; b++) Z[a][b] = (a == b) ? 1.0 : 0.0;
 	// ---- tridiagonalisation: reflection k clears A[k+2.., k]
 #pragma unroll
-	for (int k = 0; k < 4; k++) {
+	for (int k = 0; k < M - 2; k++) {
 		double sigma = 0.0;
 #pragma unroll
-		for (int r = k + 2; r < 6; r++) sigma += A[r][k] * A[r][k];
+		for (int r = k + 2; r < M; r++) sigma += A[r][k] * A[r][k];
 		const double x0 = A[k + 1][k];
 		if (sigma > kTiny) {
 			const double nrm = EIG6_SQRT(x0 * x0 + sigma);
 			const double alpha = (x0 >= 0.0) ? -nrm : nrm;
-			double v[6];
+			double v[M];
 #pragma unroll
-			for (int r = 0; r < 6; r++) v[r] = (r == k + 1) ? x0 - alpha : (r > k + 1 ? A[r][k] : 0.0);
+			for (int r = 0; r < M; r++) v[r] = (r == k + 1) ? x0 - alpha : (r > k + 1 ? A[r][k] : 0.0);
 			const double beta = 2.0 * EIG6_RCP(v[k + 1] * v[k + 1] + sigma);
-			double pv[6], K = 0.0;
+			double pv[M], K = 0.0;
 #pragma unroll
-			for (int r = k + 1; r < 6; r++) {
+			for (int r = k + 1; r < M; r++) {
 				double s = 0.0;
 #pragma unroll
-				for (int c = k + 1; c < 6; c++) s += A[r][c] * v[c];
+				for (int c = k + 1; c < M; c++) s += A[r][c] * v[c];
 				pv[r] = beta * s;
 				K += pv[r] * v[r];
 			}
 			K *= 0.5 * beta;
 #pragma unroll
-			for (int r = k + 1; r < 6; r++) pv[r] -= K * v[r];	// w
+			for (int r = k + 1; r < M; r++) pv[r] -= K * v[r];	// w
 #pragma unroll
-			for (int r = k + 1; r < 6; r++)
+			for (int r = k + 1; r < M; r++)
 #pragma unroll
 				for (int c = k + 1; c <= r; c++) {
 					const double t = A[r][c] - v[r] * pv[c] - pv[r] * v[c];
@@ -72,33 +75,33 @@ EIG6_HD void sym_eig6(double (&A)[6][6], double (&Z)[6][6], double (&d)[6]) {
 			A[k + 1][k] = alpha;
 			// Z <- Z H
 #pragma unroll
-			for (int r = 0; r < 6; r++) {
+			for (int r = 0; r < M; r++) {
 				double s = 0.0;
 #pragma unroll
-				for (int c = k + 1; c < 6; c++) s += Z[r][c] * v[c];
+				for (int c = k + 1; c < M; c++) s += Z[r][c] * v[c];
 				s *= beta;
 #pragma unroll
-				for (int c = k + 1; c < 6; c++) Z[r][c] -= s * v[c];
+				for (int c = k + 1; c < M; c++) Z[r][c] -= s * v[c];
 			}
 		}
 	}
 #pragma unroll
-	for (int k = 0; k < 6; k++) {
+	for (int k = 0; k < M; k++) {
 		d[k] = A[k][k];
-		e[k] = (k < 5) ? A[k + 1 < 6 ? k + 1 : 5][k] : 0.0;
+		e[k] = (k < M - 1) ? A[k + 1 < M ? k + 1 : M - 1][k] : 0.0;
 	}
 	// ---- implicit QL: e[i] couples i and i + 1
 #pragma unroll
-	for (int l = 0; l < 5; l++) {
+	for (int l = 0; l < M - 1; l++) {
 		for (int iter = 0; iter < 40; iter++) {
-			int m = 5;
+			int m = M - 1;
 #pragma unroll
-			for (int mm = 4; mm >= l; mm--)
+			for (int mm = M - 2; mm >= l; mm--)
 				if (fabs(e[mm]) <= kEps * (fabs(d[mm]) + fabs(d[mm + 1]))) m = mm;
 			if (m == l) break;
-			double dm = d[5];
+			double dm = d[M - 1];
 #pragma unroll
-			for (int mm = 4; mm > l; mm--)
+			for (int mm = M - 2; mm > l; mm--)
 				if (m == mm) dm = d[mm];
 			double g = (d[l + 1] - d[l]) * (0.5 * EIG6_RCP(e[l]));
 			double r = EIG6_SQRT(g * g + 1.0);
@@ -106,7 +109,7 @@ EIG6_HD void sym_eig6(double (&A)[6][6], double (&Z)[6][6], double (&d)[6]) {
 			double s = 1.0, c = 1.0, p = 0.0;
 			bool under = false;
 #pragma unroll
-			for (int i = 4; i >= l; i--) {
+			for (int i = M - 2; i >= l; i--) {
 				if (i < m && !under) {
 					const double f = s * e[i], b = c * e[i];
 					const double r2 = f * f + g * g;
@@ -126,7 +129,7 @@ EIG6_HD void sym_eig6(double (&A)[6][6], double (&Z)[6][6], double (&d)[6]) {
 						d[i + 1] = g + p;
 						g = c * r - b;
 #pragma unroll
-						for (int k = 0; k < 6; k++) {
+						for (int k = 0; k < M; k++) {
 							const double zk = Z[k][i + 1];
 							Z[k][i + 1] = s * Z[k][i] + c * zk;
 							Z[k][i] = c * Z[k][i] - s * zk;
@@ -139,10 +142,12 @@ EIG6_HD void sym_eig6(double (&A)[6][6], double (&Z)[6][6], double (&d)[6]) {
 				e[l] = g;
 			}
 #pragma unroll
-			for (int mm = 5; mm > l; mm--)
+			for (int mm = M - 1; mm > l; mm--)
 				if (m == mm) e[mm] = 0.0;
 		}
 	}
 }
+
+EIG6_HD void sym_eig6(double (&A)[6][6], double (&Z)[6][6], double (&d)[6]) { sym_eig<6>(A, Z, d); }
 
 }  // namespace osc

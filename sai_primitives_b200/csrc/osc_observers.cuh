@@ -105,10 +105,10 @@ static __device__ __noinline__ void task_nullspace_one(const OscProgram& P, cons
 		for (int a = 0; a < k; a++)
 			for (int j = 0; j < N; j++) S[a * N + j] = jt.S[a][j];
 		mm(S, k, n, Nprec, n, Jp);
-		double Ur[N * N], sr[N], Vr[N * N];
+		double Ur[N * N], sr[N];
 		int kr = 0;
 		if (sqrt(fro2(Jp, k * n)) >= 1e-3) {
-			svd_thin(Jp, k, n, Ur, sr, Vr);
+			left_svd_gram<N>(Jp, k, n, Ur, sr);
 			if (sr[0] >= 1e-3) {
 				kr = k;
 				for (int c = k - 1; c > 0; c--) {

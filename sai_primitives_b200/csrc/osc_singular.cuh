@@ -1,6 +1,6 @@
 // The singular / blending path: robots whose task Jacobian fails the sound non-singularity test of the
 // fast kernel are appended to a compacted list and re-evaluated here, one robot per thread, following the
-// reference statement by statement with an explicit thin SVD (one-sided Jacobi):
+// reference statement by statement with an explicit thin SVD (from the eigen-decomposition of the Gram matrix, osc_eig6.h):
 //   SingularityHandler::updateTaskModel     src/tasks/SingularityHandler.cpp:75-228
 //   SingularityHandler::classifySingularity src/tasks/SingularityHandler.cpp:230-295 (stateful)
 //   SingularityHandler::computeTorques      src/tasks/SingularityHandler.cpp:297-368
@@ -142,87 +142,10 @@ static __device__ __noinline__ bool spd_inverse(const double* A, int n, double* 
 	return ok;
 }
 
-// Thin SVD of A (m x n, row-major), k = min(m, n):  A = U diag(s) V^T,  U m x k, V n x k, s descending.
-// One-sided Jacobi on the side with fewer columns.  Sign convention of this repo:
-// the largest-magnitude entry of every column of V is positive.
-static __device__ __noinline__ void svd_thin(const double* A, int m, int n, double* U, double* s, double* V) {
-	const bool tr = m < n;	// work on W = tr ? A^T : A, shape wr x wc with wr >= wc
-	const int wr = tr ? n : m, wc = tr ? m : n;
-	double W[MAXD * MAXD], Z[MAXD * MAXD];
-	for (int i = 0; i < wr; i++)
-		for (int j = 0; j < wc; j++) W[i * wc + j] = tr ? A[j * n + i] : A[i * n + j];
-	for (int i = 0; i < wc; i++)
-		for (int j = 0; j < wc; j++) Z[i * wc + j] = (i == j) ? 1.0 : 0.0;
-	for (int sweep = 0; sweep < 40; sweep++) {
-		bool rotated = false;
-		for (int p = 0; p < wc - 1; p++)
-			for (int q = p + 1; q < wc; q++) {
-				double al = 0.0, be = 0.0, ga = 0.0;
-				for (int i = 0; i < wr; i++) {
-					al += W[i * wc + p] * W[i * wc + p];
-					be += W[i * wc + q] * W[i * wc + q];
-					ga += W[i * wc + p] * W[i * wc + q];
-				}
-				// stop at the rounding floor of the rotations (a 1e-16 threshold is below it and never met: all 40 sweeps ran)
-				if (ga == 0.0 || fabs(ga) <= 2e-15 * sqrt(al * be)) continue;
-				rotated = true;
-				const double zeta = (be - al) / (2.0 * ga);
-				const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-				const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
-				for (int i = 0; i < wr; i++) {
-					const double a = W[i * wc + p], b = W[i * wc + q];
-					W[i * wc + p] = c * a - sn * b;
-					W[i * wc + q] = sn * a + c * b;
-				}
-				for (int i = 0; i < wc; i++) {
-					const double a = Z[i * wc + p], b = Z[i * wc + q];
-					Z[i * wc + p] = c * a - sn * b;
-					Z[i * wc + q] = sn * a + c * b;
-				}
-			}
-		if (!rotated) break;
-	}
-	double nrm[MAXD];
-	int order[MAXD];
-	for (int j = 0; j < wc; j++) {
-		double t = 0.0;
-		for (int i = 0; i < wr; i++) t += W[i * wc + j] * W[i * wc + j];
-		nrm[j] = sqrt(t);
-		order[j] = j;
-	}
-	for (int a = 0; a < wc - 1; a++)  // stable selection sort, descending
-		for (int b = wc - 1; b > a; b--)
-			if (nrm[order[b]] > nrm[order[b - 1]]) {
-				const int t = order[b];
-				order[b] = order[b - 1];
-				order[b - 1] = t;
-			}
-	const int k = wc;
-	for (int jj = 0; jj < k; jj++) {
-		const int j = order[jj];
-		s[jj] = nrm[j];
-		const double inv = nrm[j] > 0.0 ? 1.0 / nrm[j] : 0.0;
-		// left factor of W: columns W[:, j] / s (wr long); right factor: Z[:, j] (wc long)
-		double* big = tr ? V : U;	 // wr x k
-		double* small = tr ? U : V;	 // wc x k
-		for (int i = 0; i < wr; i++) big[i * k + jj] = W[i * wc + j] * inv;
-		for (int i = 0; i < wc; i++) small[i * k + jj] = Z[i * wc + j];
-	}
-	for (int jj = 0; jj < k; jj++) {
-		int im = 0;
-		for (int i = 1; i < n; i++)
-			if (fabs(V[i * k + jj]) > fabs(V[im * k + jj])) im = i;
-		if (V[im * k + jj] < 0.0) {
-			for (int i = 0; i < n; i++) V[i * k + jj] = -V[i * k + jj];
-			for (int i = 0; i < m; i++) U[i * k + jj] = -U[i * k + jj];
-		}
-	}
-}
-
 // Thin SVD of the six-row projected task Jacobian A (6 x n, row-major), k = min(6, n):  A = U diag(s) V^T through the
 // eigen-decomposition of the 6 x 6 Gram matrix A A^T in registers (osc_eig6.h), V = A^T U / s -- what the blending path does
-// (osc_blend.cuh), a tenth of the instructions of the one-sided Jacobi above on this shape (it was a third of the rolled general
-// path: profiles/r02_summary.md).  Same conventions: s descending, a zero singular value gets a zero column of V, the
+// (osc_blend.cuh), a tenth of the instructions of the one-sided Jacobi sweeps in local memory that did this until round 2 (a third of the
+// rolled general path: profiles/r02_summary.md).  Same conventions: s descending, a zero singular value gets a zero column of V, the
 // largest-magnitude entry of every column of V is positive.
 static __device__ __noinline__ void svd_rows6(const double* A, int n, double* U, double* s, double* V) {
 	const int k = n < 6 ? n : 6;
@@ -280,6 +203,53 @@ static __device__ __noinline__ void svd_rows6(const double* A, int n, double* U,
 #pragma unroll
 				for (int a = 0; a < 6; a++) U[a * k + jj] = -U[a * k + jj];
 			}
+		}
+	}
+}
+
+// Left singular vectors (U, k x k, row-major) and singular values (s, descending) of the joint task's projected Jacobian A
+// (k x n, k <= N) for SaiModel::matrixRangeBasis (JointTask.cpp:218-283): eigen-decomposition of the k x k Gram matrix A A^T in
+// registers, padded to N x N with -1 on the diagonal so that the padding sorts last.  The range basis only enters through
+// U^T (.) U products, so any orthonormal basis of the same subspace gives the same torques.
+template <int N>
+static __device__ __noinline__ void left_svd_gram(const double* A, int k, int n, double* U, double* s) {
+	double G[N][N], Z[N][N], d[N];
+#pragma unroll
+	for (int a = 0; a < N; a++)
+#pragma unroll
+		for (int b = 0; b <= a; b++) {
+			double t = (a == b) ? -1.0 : 0.0;
+			if (a < k && b < k) {
+				t = 0.0;
+				for (int j = 0; j < n; j++) t += A[a * n + j] * A[b * n + j];
+			}
+			G[a][b] = t;
+			G[b][a] = t;
+		}
+	sym_eig<N>(G, Z, d);
+#pragma unroll
+	for (int a = 0; a < N - 1; a++)
+#pragma unroll
+		for (int b = a + 1; b < N; b++) {
+			if (d[b] > d[a]) {
+				const double td = d[a];
+				d[a] = d[b];
+				d[b] = td;
+#pragma unroll
+				for (int r = 0; r < N; r++) {
+					const double tz = Z[r][a];
+					Z[r][a] = Z[r][b];
+					Z[r][b] = tz;
+				}
+			}
+		}
+#pragma unroll
+	for (int c = 0; c < N; c++) {
+		if (c < k) {
+			s[c] = sqrt(fmax(d[c], 0.0));
+#pragma unroll
+			for (int a = 0; a < N; a++)
+				if (a < k) U[a * k + c] = Z[a][c];
 		}
 	}
 }
@@ -610,10 +580,10 @@ static __device__ __noinline__ void generic_cycle_one(const OscProgram& P, const
 				for (int j = 0; j < N; j++) S[a * N + j] = jt.S[a][j];
 			mm(S, k, n, Nprec, n, Jp);	// _projected_jacobian (k x n)
 			// range basis (SaiModel::matrixRangeBasis, tolerance 1e-3)
-			double Ur[N * N], sr[N], Vr[N * N];
+			double Ur[N * N], sr[N];
 			int kr = 0;
 			if (sqrt(fro2(Jp, k * n)) >= 1e-3) {
-				svd_thin(Jp, k, n, Ur, sr, Vr);	 // Ur: k x min(k,n) = k x k
+				left_svd_gram<N>(Jp, k, n, Ur, sr);	 // Ur: k x k
 				if (sr[0] >= 1e-3) {
 					kr = k;
 					for (int c = k - 1; c > 0; c--) {

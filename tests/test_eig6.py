@@ -17,6 +17,7 @@ def probe(tmp_path_factory):
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", str(out), os.path.join(HERE, "cpp", "eig6_host_probe.cpp")])
     lib = C.CDLL(str(out))
     lib.eig6_probe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.eig_probe_m.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -72,3 +73,26 @@ def test_degenerate_inputs(probe):
         assert np.allclose(np.sort(d[k]), lam, atol=1e-14 * max(1.0, np.abs(lam).max()))
         assert np.abs(Z[k].T @ Z[k] - np.eye(6)).max() <= 1e-14
         assert np.abs(G[k] @ Z[k] - Z[k] * d[k]).max() <= 1e-14 * max(1.0, np.abs(lam).max())
+
+
+@pytest.mark.parametrize("M", [4, 7, 8])
+def test_other_sizes_projector_like_matrices(probe, M):
+    """the rolled general path takes the range basis of the joint task's projected Jacobian from sym_eig<number of joints>: Gram
+    matrices of null-space projectors (eigenvalues 0 and >= 1, repeated) and of random matrices"""
+    rng = np.random.default_rng(M)
+    mats = []
+    for k in range(200):
+        r = int(rng.integers(1, M))
+        J = rng.standard_normal((r, M)); Mi = np.linalg.inv(np.diag(rng.uniform(0.5, 2.0, M)) + 0.1 * np.ones((M, M)))
+        Nn = np.eye(M) - Mi @ J.T @ np.linalg.inv(J @ Mi @ J.T) @ J          # dynamically consistent null-space projector
+        B = Nn if k % 2 == 0 else rng.standard_normal((M, M))
+        mats.append(B @ B.T)
+    G = np.ascontiguousarray(np.array([0.5 * (g + g.T) for g in mats]))
+    Z = np.zeros((len(mats), M, M)); d = np.zeros((len(mats), M))
+    probe.eig_probe_m(M, G.ctypes.data, len(mats), Z.ctypes.data, d.ctypes.data)
+    for k in range(len(mats)):
+        lam = np.linalg.eigvalsh(G[k])
+        scale = max(1.0, lam[-1])
+        assert np.abs(np.sort(d[k]) - lam).max() <= 1e-13 * scale
+        assert np.abs(Z[k].T @ Z[k] - np.eye(M)).max() <= 1e-13
+        assert np.abs(G[k] @ Z[k] - Z[k] * d[k]).max() <= 1e-13 * scale
